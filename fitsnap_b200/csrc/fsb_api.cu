@@ -1,0 +1,171 @@
+// C-ABI entry points of libfitsnap_b200.so (declared in include/fitsnap_b200.h).
+// Argument validation + dispatch to the kernel launchers; never throws, never syncs.
+#include "fsb_common.cuh"
+#include <string.h>
+#include <stdio.h>
+#include <new>
+
+// launchers (gram.cu, solve.cu, stream_ops.cu)
+size_t fsb_factor_bytes_impl(int k);
+int fsb_launch_factor(const fsb_context* h, const double* gaug, int k, double alpha, void* factor,
+                      size_t factor_bytes, int32_t* info, cudaStream_t s);
+int fsb_launch_factor_solve(const fsb_context* h, const void* factor, int k, const double* rhs,
+                            int64_t rhs_stride, double alpha, const double* x_in, double* x_out,
+                            cudaStream_t s);
+size_t fsb_residual_ws_bytes(const fsb_context* h, int64_t n_rows, int k);
+int fsb_launch_residual(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* w,
+                        const uint8_t* testing, int64_t n_rows, int k, const double* x, double* g, void* ws,
+                        size_t ws_bytes, cudaStream_t s);
+int fsb_launch_predict(const fsb_context* h, const double* A, int64_t lda, int64_t n_rows, int k,
+                       const double* x, double* y, cudaStream_t s);
+int fsb_launch_scatter(const fsb_context* h, const double* raw, const int64_t* raw_row_off,
+                       const int64_t* out_row_off, const int32_t* natoms, const double* volume,
+                       const double* energy, const double* forces, const double* stress,
+                       const double* eweight, const double* fweight, const double* vweight,
+                       const double* type_fraction, const double* blank2j, int ncfg, int numtypes,
+                       int ncoeff, int flags, double* A, int64_t lda, double* b, double* w,
+                       int32_t* nonfinite, int64_t n_rows_hint, cudaStream_t s);
+
+static thread_local char g_cuda_err[512] = "";
+
+void fsb_note_cuda_error(cudaError_t e, const char* where) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+static const int FSB_MAX_K = 2047;  // rowpass kernels hold ceil(k/32) <= 64 values per lane
+
+extern "C" {
+
+int fsb_version(void) { return 100; }
+
+const char* fsb_status_string(int status) {
+  switch (status) {
+    case FSB_OK: return "ok";
+    case FSB_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case FSB_ERR_CUDA: return "CUDA error";
+    case FSB_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+    case FSB_ERR_UNSUPPORTED: return "unsupported size or configuration";
+    case FSB_ERR_NO_DEVICE: return "no usable CUDA device";
+    default: return "unknown status";
+  }
+}
+
+const char* fsb_last_cuda_error(void) { return g_cuda_err; }
+
+int fsb_create(fsb_handle_t* out, int device) {
+  if (!out) return FSB_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    if (e != cudaSuccess) fsb_note_cuda_error(e, "cudaGetDeviceCount");
+    return FSB_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) return FSB_ERR_INVALID_ARGUMENT;
+  FSB_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FSB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d is sm_%d%d; this library is built for sm_100a only",
+             device, prop.major, prop.minor);
+    return FSB_ERR_UNSUPPORTED;
+  }
+  fsb_context* h = new (std::nothrow) fsb_context;
+  if (!h) return FSB_ERR_INVALID_ARGUMENT;
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  *out = h;
+  return FSB_OK;
+}
+
+int fsb_destroy(fsb_handle_t h) {
+  delete h;
+  return FSB_OK;
+}
+
+int fsb_sm_count(fsb_handle_t h, int* sm_count) {
+  if (!h || !sm_count) return FSB_ERR_INVALID_ARGUMENT;
+  *sm_count = h->sm_count;
+  return FSB_OK;
+}
+
+int fsb_scatter(fsb_handle_t h, const double* raw, const int64_t* raw_row_off, const int64_t* out_row_off,
+                const int32_t* natoms, const double* volume, const double* energy, const double* forces,
+                const double* stress, const double* eweight, const double* fweight, const double* vweight,
+                const double* type_fraction, const double* blank2j, int32_t ncfg, int32_t numtypes,
+                int32_t ncoeff, int32_t flags, double* A, int64_t lda, double* b, double* w,
+                int64_t n_rows_out, int32_t* nonfinite, void* stream) {
+  if (!h || ncfg < 0 || numtypes < 1 || ncoeff < 1 || n_rows_out < 0) return FSB_ERR_INVALID_ARGUMENT;
+  if (ncfg == 0 || n_rows_out == 0) return FSB_OK;
+  if (!raw || !raw_row_off || !out_row_off || !natoms || !blank2j || !A || !b || !w)
+    return FSB_ERR_INVALID_ARGUMENT;
+  const bool bzero = flags & FSB_BZEROFLAG;
+  const int k = ncoeff * numtypes + (bzero ? 0 : numtypes);
+  if (lda < k) return FSB_ERR_INVALID_ARGUMENT;
+  if ((flags & FSB_ROWS_ENERGY) && (!energy || !eweight || (!bzero && !type_fraction)))
+    return FSB_ERR_INVALID_ARGUMENT;
+  if ((flags & FSB_ROWS_FORCE) && (!forces || !fweight)) return FSB_ERR_INVALID_ARGUMENT;
+  if ((flags & FSB_ROWS_STRESS) && (!stress || !vweight || !volume)) return FSB_ERR_INVALID_ARGUMENT;
+  return fsb_launch_scatter(h, raw, raw_row_off, out_row_off, natoms, volume, energy, forces, stress, eweight,
+                            fweight, vweight, type_fraction, blank2j, ncfg, numtypes, ncoeff, flags, A, lda, b,
+                            w, nonfinite, n_rows_out, (cudaStream_t)stream);
+}
+
+size_t fsb_gram_workspace_bytes(fsb_handle_t h, int64_t n_rows, int32_t k) {
+  if (!h || k < 1 || n_rows < 0) return 0;
+  return fsb_gram_ws_bytes(h, n_rows, k);
+}
+
+int fsb_gram(fsb_handle_t h, const double* A, int64_t lda, const double* b, const double* w,
+             const uint8_t* testing, int64_t n_rows, int32_t k, double* gaug, void* workspace,
+             size_t workspace_bytes, void* stream) {
+  if (!h || k < 1 || k > FSB_MAX_K || n_rows < 0 || lda < k || !gaug || !workspace)
+    return FSB_ERR_INVALID_ARGUMENT;
+  if (n_rows > 0 && (!A || !b || !w)) return FSB_ERR_INVALID_ARGUMENT;
+  return fsb_launch_gram(h, A, lda, b, w, testing, n_rows, k, gaug, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
+}
+
+size_t fsb_factor_bytes(fsb_handle_t h, int32_t k) {
+  if (!h || k < 1) return 0;
+  return fsb_factor_bytes_impl(k);
+}
+
+int fsb_factor(fsb_handle_t h, const double* gaug, int32_t k, double alpha, void* factor,
+               size_t factor_bytes, int32_t* info, void* stream) {
+  if (!h || !gaug || k < 1 || k > FSB_MAX_K || !factor || !info || !(alpha >= 0.0))
+    return FSB_ERR_INVALID_ARGUMENT;
+  return fsb_launch_factor(h, gaug, k, alpha, factor, factor_bytes, info, (cudaStream_t)stream);
+}
+
+int fsb_factor_solve(fsb_handle_t h, const void* factor, int32_t k, const double* rhs, int64_t rhs_stride,
+                     double alpha, const double* x_in, double* x_out, void* stream) {
+  if (!h || !factor || k < 1 || k > FSB_MAX_K || !rhs || rhs_stride < 1 || !x_out)
+    return FSB_ERR_INVALID_ARGUMENT;
+  return fsb_launch_factor_solve(h, factor, k, rhs, rhs_stride, alpha, x_in, x_out, (cudaStream_t)stream);
+}
+
+size_t fsb_residual_workspace_bytes(fsb_handle_t h, int64_t n_rows, int32_t k) {
+  if (!h || k < 1 || n_rows < 0) return 0;
+  return fsb_residual_ws_bytes(h, n_rows, k);
+}
+
+int fsb_residual(fsb_handle_t h, const double* A, int64_t lda, const double* b, const double* w,
+                 const uint8_t* testing, int64_t n_rows, int32_t k, const double* x, double* g,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || k < 1 || k > FSB_MAX_K || n_rows < 0 || lda < k || !x || !g || !workspace)
+    return FSB_ERR_INVALID_ARGUMENT;
+  if (n_rows > 0 && (!A || !b || !w)) return FSB_ERR_INVALID_ARGUMENT;
+  return fsb_launch_residual(h, A, lda, b, w, testing, n_rows, k, x, g, workspace, workspace_bytes,
+                             (cudaStream_t)stream);
+}
+
+int fsb_predict(fsb_handle_t h, const double* A, int64_t lda, int64_t n_rows, int32_t k, const double* x,
+                double* y, void* stream) {
+  if (!h || k < 1 || k > FSB_MAX_K || n_rows < 0 || lda < k || !x) return FSB_ERR_INVALID_ARGUMENT;
+  if (n_rows > 0 && (!A || !y)) return FSB_ERR_INVALID_ARGUMENT;
+  return fsb_launch_predict(h, A, lda, n_rows, k, x, y, (cudaStream_t)stream);
+}
+
+}  // extern "C"

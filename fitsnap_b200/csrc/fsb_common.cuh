@@ -1,0 +1,53 @@
+// Shared declarations of the fitsnap_b200 native library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/fitsnap_b200.h"
+
+struct fsb_context {
+  int device;
+  int sm_count;
+  size_t smem_optin;   // max dynamic shared memory per block (opt-in)
+};
+
+// thread-local last CUDA error text (fsb_last_cuda_error)
+void fsb_note_cuda_error(cudaError_t e, const char* where);
+
+#define FSB_CUDA_TRY(expr)                                   \
+  do {                                                       \
+    cudaError_t _e = (expr);                                 \
+    if (_e != cudaSuccess) {                                 \
+      fsb_note_cuda_error(_e, #expr);                        \
+      return FSB_ERR_CUDA;                                   \
+    }                                                        \
+  } while (0)
+
+#define FSB_LAUNCH_CHECK(where)                              \
+  do {                                                       \
+    cudaError_t _e = cudaGetLastError();                     \
+    if (_e != cudaSuccess) {                                 \
+      fsb_note_cuda_error(_e, where);                        \
+      return FSB_ERR_CUDA;                                   \
+    }                                                        \
+  } while (0)
+
+static inline int64_t fsb_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t fsb_round_up(int64_t a, int64_t b) { return fsb_ceil_div(a, b) * b; }
+
+// ---- geometry shared by host planners and kernels --------------------------------------
+// Gram: output is tiled in GT x GT super-tiles of the augmented (k+1)x(k+1) matrix; only
+// lower-triangular super-tiles are computed.
+constexpr int FSB_GT = 128;          // super-tile edge (columns of A)
+constexpr int FSB_GRCH = 16;         // rows of A staged in shared memory per pipeline step
+constexpr int FSB_GLDS = FSB_GT + 4; // smem row pitch in doubles: == 4 (mod 16) -> conflict-free DMMA fragment loads
+constexpr int FSB_GTHREADS = 512;    // 16 warps, each owning a 32x32 sub-tile (4x4 DMMA 8x8 blocks)
+
+// Cholesky panel width
+constexpr int FSB_NB = 64;
+
+// launchers implemented in the individual .cu files
+int fsb_launch_gram(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* w,
+                    const uint8_t* testing, int64_t n_rows, int k, double* gaug, void* ws, size_t ws_bytes,
+                    cudaStream_t s);
+size_t fsb_gram_ws_bytes(const fsb_context* h, int64_t n_rows, int k);

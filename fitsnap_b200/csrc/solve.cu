@@ -1,0 +1,354 @@
+// K6: equilibrated Cholesky factorisation of (G + alpha I) and triangular solves, fp64.
+//
+// Replaces, on the reduced (k x k) system, what the reference delegates to LAPACK:
+//   scipy.linalg.lstsq(aw, bw, 1.0e-13)            fitsnap3lib/solvers/svd.py:54
+//   sklearn Ridge(alpha, fit_intercept=False).fit  fitsnap3lib/solvers/ridge.py:49-57
+//   inv(XtX + alpha I) @ Xty                       fitsnap3lib/lib/ridge_solver/regressor.py:10-16
+// The accuracy lost by squaring the condition number is recovered by iterative refinement
+// with a residual streamed from A itself (stream_ops.cu, fsb_residual); see DESIGN.md.
+//
+// Layout of the caller-owned `factor` buffer (doubles), kp = round_up(k, 64):
+//   d[kp]      power-of-two column scales (0 => coefficient pinned to 0)
+//   flag[kp]   1.0 => column dropped during factorisation (pivot below tolerance)
+//   L[kp*kp]   row-major, pitch kp; lower triangle holds the Cholesky factor of S = D (G+alpha I) D
+//
+// The factorisation is a right-looking blocked Cholesky with 64-wide panels, three small
+// kernels per panel (diag potrf / panel trsm / trailing syrk).  k <= 1024 means <= 48
+// launches of latency-bound work (k^3/3 = 0.36 GFLOP at k = 1024): negligible next to the
+// Gram pass, so it is written for robustness, not peak.
+#include "fsb_common.cuh"
+#include <float.h>
+
+namespace {
+
+constexpr int NB = FSB_NB;
+constexpr int NBP = NB + 1;  // padded smem pitch
+
+struct FactorView {
+  double* d;
+  double* flag;
+  double* L;
+  int kp;
+};
+
+__host__ __device__ inline FactorView view_factor(void* buf, int k) {
+  FactorView v;
+  v.kp = ((k + NB - 1) / NB) * NB;
+  if (v.kp == 0) v.kp = NB;
+  v.d = (double*)buf;
+  v.flag = v.d + v.kp;
+  v.L = v.flag + v.kp;
+  return v;
+}
+
+__device__ __forceinline__ double pow2_scale(double g) {
+  // d = 2^-floor(e/2) with g = m 2^e, m in [0.5,1)  =>  g d^2 in [0.5, 2)
+  int e;
+  frexp(g, &e);
+  int h = (e >= 0) ? (e / 2) : -((-e + 1) / 2);
+  return ldexp(1.0, -h);
+}
+
+// S = D (G + alpha I) D on the lower triangle; padding rows/cols get the identity.
+__global__ void equilibrate_kernel(const double* __restrict__ gaug, int k, double alpha, FactorView f,
+                                   int32_t* info) {
+  const int i = blockIdx.x;
+  const int ka = k + 1;
+  const int kp = f.kp;
+  double gii = 0.0, di = 0.0;
+  if (i < k) {
+    gii = gaug[(size_t)i * ka + i] + alpha;
+    di = (gii > 0.0 && gii < DBL_MAX) ? pow2_scale(gii) : 0.0;
+  }
+  if (threadIdx.x == 0) {
+    f.d[i] = di;
+    f.flag[i] = 0.0;
+    if (i < k && di == 0.0) atomicAdd(&info[FSB_INFO_NUM_PINNED], 1);
+  }
+  for (int j = threadIdx.x; j <= i; j += blockDim.x) {
+    double v;
+    if (i >= k || di == 0.0) {
+      v = (i == j) ? 1.0 : 0.0;
+    } else {
+      const double gjj = gaug[(size_t)j * ka + j] + alpha;
+      const double dj = (gjj > 0.0 && gjj < DBL_MAX) ? pow2_scale(gjj) : 0.0;
+      if (dj == 0.0) v = 0.0;
+      else v = (i == j) ? di * gii * di : di * gaug[(size_t)i * ka + j] * dj;
+    }
+    f.L[(size_t)i * kp + j] = v;
+  }
+  // clear the strict upper part of this row so the buffer is fully defined
+  for (int j = i + 1 + threadIdx.x; j < kp; j += blockDim.x) f.L[(size_t)i * kp + j] = 0.0;
+}
+
+// Cholesky of the 64x64 diagonal block of panel p, in shared memory.
+__global__ void __launch_bounds__(256) potrf_diag_kernel(FactorView f, int p, double tol, int32_t* info) {
+  __shared__ double s[NB][NBP];
+  __shared__ int dropped[NB];
+  const int kp = f.kp;
+  double* blk = f.L + (size_t)(p * NB) * kp + p * NB;
+  for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
+    const int r = idx / NB, c = idx % NB;
+    s[r][c] = (c <= r) ? blk[(size_t)r * kp + c] : 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x < NB) dropped[threadIdx.x] = 0;
+  __syncthreads();
+  // diag(S) lies in [0.5, 2) after equilibration, so `tol` is an absolute pivot threshold.
+  for (int j = 0; j < NB; ++j) {
+    if (threadIdx.x == 0) {
+      const double piv = s[j][j];
+      if (!(piv > tol)) {
+        dropped[j] = 1;
+        s[j][j] = 1.0;
+      } else {
+        s[j][j] = sqrt(piv);
+      }
+    }
+    __syncthreads();
+    const double ljj = s[j][j];
+    const int dj = dropped[j];
+    for (int r = j + 1 + threadIdx.x; r < NB; r += blockDim.x) s[r][j] = dj ? 0.0 : s[r][j] / ljj;
+    __syncthreads();
+    if (!dj) {
+      // trailing update of the lower triangle: (r, c) with j < c <= r
+      const int m = NB - 1 - j;
+      for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+        const int r = j + 1 + idx / m, c = j + 1 + idx % m;
+        if (c <= r) s[r][c] -= s[r][j] * s[c][j];
+      }
+    }
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
+    const int r = idx / NB, c = idx % NB;
+    if (c <= r) blk[(size_t)r * kp + c] = s[r][c];
+  }
+  if (threadIdx.x < NB && dropped[threadIdx.x]) {
+    const int col = p * NB + threadIdx.x;
+    f.flag[col] = 1.0;
+    f.d[col] = 0.0;
+    atomicAdd(&info[FSB_INFO_NUM_DEFICIENT], 1);
+    atomicExch(&info[FSB_INFO_STATUS], 1);
+    atomicMin(&info[FSB_INFO_FIRST_BAD_COLUMN], col);
+  }
+}
+
+// Panel solve: rows of block-row bi (> p) against L_pp^T.  One thread per row, row in registers.
+__global__ void __launch_bounds__(NB) trsm_panel_kernel(FactorView f, int p) {
+  __shared__ double lpp[NB][NBP];
+  __shared__ double fl[NB];
+  const int kp = f.kp;
+  const int bi = p + 1 + blockIdx.x;
+  const double* dblk = f.L + (size_t)(p * NB) * kp + p * NB;
+  for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
+    const int r = idx / NB, c = idx % NB;
+    lpp[r][c] = dblk[(size_t)r * kp + c];
+  }
+  if (threadIdx.x < NB) fl[threadIdx.x] = f.flag[p * NB + threadIdx.x];
+  __syncthreads();
+  double* row = f.L + (size_t)(bi * NB + threadIdx.x) * kp + p * NB;
+  double x[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) x[c] = row[c];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) {
+    const double xc = (fl[c] != 0.0) ? 0.0 : x[c] / lpp[c][c];
+    x[c] = xc;
+#pragma unroll
+    for (int c2 = c + 1; c2 < NB; ++c2) x[c2] -= xc * lpp[c2][c];
+  }
+#pragma unroll
+  for (int c = 0; c < NB; ++c) row[c] = x[c];
+}
+
+// Trailing update: C[bi][bj] -= L[bi][p] L[bj][p]^T for p < bj <= bi.
+__global__ void __launch_bounds__(256) syrk_update_kernel(FactorView f, int p) {
+  constexpr int MH = 32;  // inner dimension staged in halves to stay under 48 KB static smem
+  __shared__ double la[NB][MH + 1];
+  __shared__ double lb[NB][MH + 1];
+  const int kp = f.kp;
+  // decode lower-triangular tile index
+  int t = blockIdx.x;
+  int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  while (ti * (ti + 1) / 2 > t) --ti;
+  const int tj = t - ti * (ti + 1) / 2;
+  const int bi = p + 1 + ti, bj = p + 1 + tj;
+  const double* pa = f.L + (size_t)(bi * NB) * kp + p * NB;
+  const double* pb = f.L + (size_t)(bj * NB) * kp + p * NB;
+  const int tr = (threadIdx.x / 16) * 4, tc = (threadIdx.x % 16) * 4;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int mh = 0; mh < NB; mh += MH) {
+    for (int idx = threadIdx.x; idx < NB * MH; idx += blockDim.x) {
+      const int r = idx / MH, c = idx % MH;
+      la[r][c] = pa[(size_t)r * kp + mh + c];
+      lb[r][c] = pb[(size_t)r * kp + mh + c];
+    }
+    __syncthreads();
+    for (int m = 0; m < MH; ++m) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = la[tr + i][m]; b[i] = lb[tc + i][m]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+  double* pc = f.L + (size_t)(bi * NB) * kp + bj * NB;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = tr + i, c = tc + j;
+      if (bi != bj || c <= r) pc[(size_t)r * kp + c] -= acc[i][j];
+    }
+}
+
+// x_out = x_in + D L^-T L^-1 D (rhs - alpha x_in); single CTA, y kept in shared memory.
+__global__ void __launch_bounds__(256) trsv_kernel(FactorView f, int k, const double* __restrict__ rhs,
+                                                   int64_t rhs_stride, double alpha,
+                                                   const double* __restrict__ x_in, double* __restrict__ x_out) {
+  extern __shared__ double sm[];
+  const int kp = f.kp;
+  double* y = sm;                 // kp
+  double* blk = sm + kp;          // NB x NBP
+  const int np = kp / NB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+
+  for (int i = tid; i < kp; i += blockDim.x) {
+    double r = 0.0;
+    if (i < k) {
+      const double xi = x_in ? x_in[i] : 0.0;
+      r = f.d[i] * (rhs[(size_t)i * rhs_stride] - alpha * xi);
+    }
+    y[i] = r;
+  }
+  __syncthreads();
+
+  // ---- forward: L y = r
+  for (int p = 0; p < np; ++p) {
+    const double* dblk = f.L + (size_t)(p * NB) * kp + p * NB;
+    for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
+      const int r = idx / NB, c = idx % NB;
+      blk[r * NBP + c] = dblk[(size_t)r * kp + c];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double* yp = y + p * NB;
+      for (int c = 0; c < NB; ++c) {
+        double part = 0.0;
+        for (int m = lane; m < c; m += 32) part += blk[c * NBP + m] * yp[m];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) {
+          const double v = (yp[c] - part) / blk[c * NBP + c];
+          yp[c] = (f.flag[p * NB + c] != 0.0) ? 0.0 : v;
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // update the remaining right-hand side: warp per row, lanes across the 64 panel columns
+    const double y0 = y[p * NB + lane], y1 = y[p * NB + 32 + lane];
+    for (int i = (p + 1) * NB + warp; i < kp; i += nwarp) {
+      const double* lrow = f.L + (size_t)i * kp + p * NB;
+      double part = lrow[lane] * y0 + lrow[32 + lane] * y1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == 0) y[i] -= part;
+    }
+    __syncthreads();
+  }
+
+  // ---- backward: L^T z = y
+  for (int p = np - 1; p >= 0; --p) {
+    const double* dblk = f.L + (size_t)(p * NB) * kp + p * NB;
+    for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
+      const int r = idx / NB, c = idx % NB;
+      blk[r * NBP + c] = dblk[(size_t)r * kp + c];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double* yp = y + p * NB;
+      for (int c = NB - 1; c >= 0; --c) {
+        double part = 0.0;
+        for (int m = c + 1 + lane; m < NB; m += 32) part += blk[m * NBP + c] * yp[m];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) yp[c] = (yp[c] - part) / blk[c * NBP + c];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // y[j] -= sum_r L[p*NB + r][j] z[r] for j < p*NB: thread per column (coalesced over j)
+    for (int j = tid; j < p * NB; j += blockDim.x) {
+      double part = 0.0;
+      const double* lcol = f.L + (size_t)(p * NB) * kp + j;
+#pragma unroll 8
+      for (int r = 0; r < NB; ++r) part += lcol[(size_t)r * kp] * y[p * NB + r];
+      y[j] -= part;
+    }
+    __syncthreads();
+  }
+
+  for (int i = tid; i < k; i += blockDim.x) {
+    const double xi = x_in ? x_in[i] : 0.0;
+    x_out[i] = xi + f.d[i] * y[i];
+  }
+}
+
+__global__ void init_info_kernel(int32_t* info, int k) {
+  if (threadIdx.x < FSB_INFO_LEN) info[threadIdx.x] = (threadIdx.x == FSB_INFO_FIRST_BAD_COLUMN) ? k : 0;
+}
+
+}  // namespace
+
+size_t fsb_factor_bytes_impl(int k) {
+  int kp = ((k + NB - 1) / NB) * NB;
+  if (kp == 0) kp = NB;
+  return ((size_t)2 * kp + (size_t)kp * kp) * sizeof(double);
+}
+
+int fsb_launch_factor(const fsb_context* h, const double* gaug, int k, double alpha, void* factor,
+                      size_t factor_bytes, int32_t* info, cudaStream_t s) {
+  (void)h;
+  if (factor_bytes < fsb_factor_bytes_impl(k)) return FSB_ERR_WORKSPACE_TOO_SMALL;
+  FactorView f = view_factor(factor, k);
+  init_info_kernel<<<1, 32, 0, s>>>(info, k);
+  FSB_LAUNCH_CHECK("init_info_kernel");
+  equilibrate_kernel<<<f.kp, 128, 0, s>>>(gaug, k, alpha, f, info);
+  FSB_LAUNCH_CHECK("equilibrate_kernel");
+  const int np = f.kp / NB;
+  const double tol = 64.0 * (double)f.kp * DBL_EPSILON;
+  for (int p = 0; p < np; ++p) {
+    potrf_diag_kernel<<<1, 256, 0, s>>>(f, p, tol, info);
+    FSB_LAUNCH_CHECK("potrf_diag_kernel");
+    const int rem = np - p - 1;
+    if (rem > 0) {
+      trsm_panel_kernel<<<rem, NB, 0, s>>>(f, p);
+      FSB_LAUNCH_CHECK("trsm_panel_kernel");
+      syrk_update_kernel<<<rem * (rem + 1) / 2, 256, 0, s>>>(f, p);
+      FSB_LAUNCH_CHECK("syrk_update_kernel");
+    }
+  }
+  return FSB_OK;
+}
+
+int fsb_launch_factor_solve(const fsb_context* h, const void* factor, int k, const double* rhs,
+                            int64_t rhs_stride, double alpha, const double* x_in, double* x_out,
+                            cudaStream_t s) {
+  FactorView f = view_factor(const_cast<void*>(factor), k);
+  const size_t smem = ((size_t)f.kp + NB * NBP) * sizeof(double);
+  if (smem > h->smem_optin) return FSB_ERR_UNSUPPORTED;
+  FSB_CUDA_TRY(cudaFuncSetAttribute(trsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  trsv_kernel<<<1, 256, smem, s>>>(f, k, rhs, rhs_stride, alpha, x_in, x_out);
+  FSB_LAUNCH_CHECK("trsv_kernel");
+  return FSB_OK;
+}

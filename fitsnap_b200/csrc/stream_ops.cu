@@ -1,0 +1,312 @@
+// HBM-bound streaming kernels of the linear-fit path:
+//   K1  scatter   raw LAMMPS descriptor blocks -> rows of A, b, w
+//                 (fitsnap3lib/calculators/lammps_snap.py:391-556, lammps_pace.py:369-509)
+//   K7  residual  g = aw^T (bw - aw x)         (refinement pass; cf. solvers/ridge.py:60)
+//       predict   y = A x                      (solvers/solver.py:377)
+// One warp owns one row: lanes stride across the columns, so every global access is a
+// coalesced 256-byte request; several rows per warp iteration keep enough loads in flight to
+// cover HBM latency for narrow rows.  No shared-memory staging: there is no reuse.
+#include "fsb_common.cuh"
+#include <float.h>
+
+namespace {
+
+constexpr double VIRIAL_UNIT = 1.6021765e6;  // lammps_snap.py:526
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------ K7
+template <int NPL, int RPI, bool WITH_G>
+__global__ void __launch_bounds__(256) rowpass_kernel(const double* __restrict__ A, int64_t lda,
+                                                      const double* __restrict__ b,
+                                                      const double* __restrict__ w,
+                                                      const uint8_t* __restrict__ testing, int64_t n_rows,
+                                                      int k, const double* __restrict__ x,
+                                                      double* __restrict__ out, int64_t rows_per_cta) {
+  // WITH_G: out = per-CTA partial g [gridDim.x][k];  else: out = y [n_rows]
+  extern __shared__ double sg[];  // k doubles (WITH_G only)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  double xr[NPL], gacc[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int c = lane + 32 * i;
+    xr[i] = (c < k) ? x[c] : 0.0;
+    gacc[i] = 0.0;
+  }
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  int64_t r_end = r_begin + rows_per_cta;
+  if (r_end > n_rows) r_end = n_rows;
+
+  for (int64_t r0 = r_begin + (int64_t)warp * RPI; r0 < r_end; r0 += (int64_t)nwarp * RPI) {
+    double a[RPI][NPL];
+    double wv[RPI], bv[RPI];
+#pragma unroll
+    for (int q = 0; q < RPI; ++q) {
+      const int64_t r = r0 + q;
+      bool keep = r < r_end;
+      if (WITH_G && keep && testing) keep = (testing[r] == 0);
+      wv[q] = 0.0; bv[q] = 0.0;
+      if (keep && WITH_G) { wv[q] = __ldg(w + r); bv[q] = __ldg(b + r); }
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int c = lane + 32 * i;
+        a[q][i] = (keep && c < k) ? __ldg(A + r * lda + c) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RPI; ++q) {
+      if (WITH_G) {
+        double dot = 0.0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          a[q][i] *= wv[q];              // aw = w * a, rounded as the reference does (svd.py:44)
+          dot += a[q][i] * xr[i];
+        }
+        dot = warp_sum(dot);
+        const double res = wv[q] * bv[q] - dot;   // bw - aw x
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) gacc[i] += a[q][i] * res;
+      } else {
+        double dot = 0.0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) dot += a[q][i] * xr[i];
+        dot = warp_sum(dot);
+        if (lane == 0 && r0 + q < r_end) out[r0 + q] = dot;
+      }
+    }
+  }
+
+  if (WITH_G) {
+    // fixed-order reduction over the CTA's warps, then one partial vector per CTA
+    for (int c = threadIdx.x; c < k; c += blockDim.x) sg[c] = 0.0;
+    __syncthreads();
+    for (int wv_ = 0; wv_ < nwarp; ++wv_) {
+      if (warp == wv_) {
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const int c = lane + 32 * i;
+          if (c < k) sg[c] += gacc[i];
+        }
+      }
+      __syncthreads();
+    }
+    for (int c = threadIdx.x; c < k; c += blockDim.x) out[(size_t)blockIdx.x * k + c] = sg[c];
+  }
+}
+
+__global__ void colsum_reduce_kernel(const double* __restrict__ partial, int nparts, int k,
+                                     double* __restrict__ g) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= k) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * k + c];
+  g[c] = s;
+}
+
+struct RowPlan {
+  int ncta;
+  int64_t rows_per_cta;
+};
+
+RowPlan plan_rows(const fsb_context* h, int64_t n_rows) {
+  RowPlan pl;
+  int64_t want = (int64_t)h->sm_count * 8;
+  int64_t maxc = fsb_ceil_div(n_rows > 0 ? n_rows : 1, 64);
+  if (want > maxc) want = maxc;
+  if (want < 1) want = 1;
+  pl.rows_per_cta = fsb_ceil_div(n_rows > 0 ? n_rows : 1, want);
+  pl.ncta = (int)fsb_ceil_div(n_rows > 0 ? n_rows : 1, pl.rows_per_cta);
+  return pl;
+}
+
+template <bool WITH_G>
+int launch_rowpass(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* w,
+                   const uint8_t* testing, int64_t n_rows, int k, const double* x, double* out,
+                   cudaStream_t s) {
+  RowPlan pl = plan_rows(h, n_rows);
+  const size_t smem = WITH_G ? (size_t)k * sizeof(double) : 0;
+  const int npl = (k + 31) / 32;
+#define FSB_ROWPASS(NPL, RPI)                                                                          \
+  rowpass_kernel<NPL, RPI, WITH_G><<<pl.ncta, 256, smem, s>>>(A, lda, b, w, testing, n_rows, k, x, out, \
+                                                              pl.rows_per_cta)
+  if (npl <= 1) FSB_ROWPASS(1, 8);
+  else if (npl <= 2) FSB_ROWPASS(2, 4);
+  else if (npl <= 4) FSB_ROWPASS(4, 4);
+  else if (npl <= 8) FSB_ROWPASS(8, 2);
+  else if (npl <= 16) FSB_ROWPASS(16, 1);
+  else if (npl <= 32) FSB_ROWPASS(32, 1);
+  else if (npl <= 64) FSB_ROWPASS(64, 1);
+  else return FSB_ERR_UNSUPPORTED;   // k > 2048
+#undef FSB_ROWPASS
+  FSB_LAUNCH_CHECK("rowpass_kernel");
+  return FSB_OK;
+}
+
+// ------------------------------------------------------------------------------ K1
+struct ScatterArgs {
+  const double* raw;
+  const int64_t* raw_row_off;
+  const int64_t* out_row_off;
+  const int32_t* natoms;
+  const double* volume;
+  const double* energy;
+  const double* forces;
+  const double* stress;
+  const double* eweight;
+  const double* fweight;
+  const double* vweight;
+  const double* type_fraction;
+  const double* blank2j;
+  int ncfg, numtypes, ncoeff, flags;
+  double* A;
+  int64_t lda;
+  double* b;
+  double* w;
+  int32_t* nonfinite;
+};
+
+__device__ __forceinline__ double scrub(double v, bool do_scrub, bool& bad) {
+  if (!isfinite(v)) {
+    bad = true;
+    if (do_scrub) {  // numpy.nan_to_num defaults (lammps_pace.py:401)
+      if (isnan(v)) return 0.0;
+      return v > 0 ? DBL_MAX : -DBL_MAX;
+    }
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t row0 = p.out_row_off[0];
+  const int64_t total = p.out_row_off[p.ncfg] - row0;
+  const bool use_e = p.flags & FSB_ROWS_ENERGY, use_f = p.flags & FSB_ROWS_FORCE,
+             use_s = p.flags & FSB_ROWS_STRESS, bzero = p.flags & FSB_BZEROFLAG;
+  const bool do_scrub = p.flags & FSB_SCRUB_NONFINITE;
+  const int kraw = p.ncoeff * p.numtypes;
+  const int k = bzero ? kraw : kraw + p.numtypes;
+  const int seg = p.ncoeff + 1;
+  const int64_t ldr = kraw + 1;
+  bool bad = false;
+
+  for (int64_t rr = warp_global; rr < total; rr += nwarps) {
+    const int64_t row = row0 + rr;
+    // binary search: largest c with out_row_off[c] <= row
+    int lo = 0, hi = p.ncfg - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (p.out_row_off[mid] <= row) lo = mid; else hi = mid - 1;
+    }
+    const int c = lo;
+    int64_t local = row - p.out_row_off[c];
+    const int n = p.natoms[c];
+    const double dn = (double)n;
+    int kind;  // 0 energy, 1 force, 2 virial
+    int64_t sub;
+    if (use_e && local == 0) { kind = 0; sub = 0; }
+    else {
+      if (use_e) local -= 1;
+      if (use_f && local < 3 * (int64_t)n) { kind = 1; sub = local; }
+      else { if (use_f) local -= 3 * (int64_t)n; kind = 2; sub = local; }
+    }
+    const int64_t rraw = p.raw_row_off[c] + (kind == 0 ? 0 : (kind == 1 ? 1 + sub : 1 + 3 * (int64_t)n + sub));
+    const double* src = p.raw + rraw * ldr;
+    const double vol = p.volume[c];
+    double* dst = p.A + row * p.lda;
+
+    for (int oc = lane; oc < k; oc += 32) {
+      double v;
+      int rc = oc;
+      bool lead = false;
+      int t = 0;
+      if (!bzero) {
+        t = oc / seg;
+        const int q = oc - t * seg;
+        lead = (q == 0);
+        rc = t * p.ncoeff + q - 1;
+      }
+      if (lead) {
+        v = (kind == 0) ? p.type_fraction[(size_t)c * p.numtypes + t] : 0.0;
+      } else {
+        const double rv = scrub(__ldg(src + rc), do_scrub, bad);
+        if (kind == 0) v = rv / dn;                         // lammps_snap.py:435
+        else if (kind == 1) v = rv;                         // :493
+        else v = (VIRIAL_UNIT * rv) / vol;                  // :526 (multiply first, then divide)
+      }
+      dst[oc] = v * p.blank2j[oc];                          // :466-467, :501-502, :535-536
+    }
+    if (lane == 0) {
+      const double ref = scrub(__ldg(src + kraw), do_scrub, bad);
+      double bv, wv;
+      if (kind == 0) {
+        bv = (p.energy[c] - ref) / dn;                      // :473
+        wv = p.eweight[c];
+      } else if (kind == 1) {
+        const int64_t atom0 = (p.raw_row_off[c] - p.raw_row_off[0] - 7 * (int64_t)c) / 3;
+        bv = p.forces[3 * atom0 + sub] - ref;               // :506-507
+        wv = p.fweight[c];
+      } else {
+        const int vi[6] = {0, 1, 2, 1, 0, 0}, vj[6] = {0, 1, 2, 2, 2, 1};
+        bv = p.stress[(size_t)c * 9 + vi[sub] * 3 + vj[sub]] - ref;   // :540-541
+        wv = p.vweight[c];
+      }
+      p.b[row] = bv;
+      p.w[row] = wv;
+    }
+  }
+  if (p.nonfinite && __any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(p.nonfinite, 1);
+}
+
+}  // namespace
+
+size_t fsb_residual_ws_bytes(const fsb_context* h, int64_t n_rows, int k) {
+  RowPlan pl = plan_rows(h, n_rows);
+  return (size_t)pl.ncta * k * sizeof(double);
+}
+
+int fsb_launch_residual(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* w,
+                        const uint8_t* testing, int64_t n_rows, int k, const double* x, double* g, void* ws,
+                        size_t ws_bytes, cudaStream_t s) {
+  RowPlan pl = plan_rows(h, n_rows);
+  if (ws_bytes < (size_t)pl.ncta * k * sizeof(double)) return FSB_ERR_WORKSPACE_TOO_SMALL;
+  int st = launch_rowpass<true>(h, A, lda, b, w, testing, n_rows, k, x, (double*)ws, s);
+  if (st != FSB_OK) return st;
+  colsum_reduce_kernel<<<(unsigned)fsb_ceil_div(k, 128), 128, 0, s>>>((const double*)ws, pl.ncta, k, g);
+  FSB_LAUNCH_CHECK("colsum_reduce_kernel");
+  return FSB_OK;
+}
+
+int fsb_launch_predict(const fsb_context* h, const double* A, int64_t lda, int64_t n_rows, int k,
+                       const double* x, double* y, cudaStream_t s) {
+  if (n_rows == 0) return FSB_OK;
+  return launch_rowpass<false>(h, A, lda, nullptr, nullptr, nullptr, n_rows, k, x, y, s);
+}
+
+int fsb_launch_scatter(const fsb_context* h, const double* raw, const int64_t* raw_row_off,
+                       const int64_t* out_row_off, const int32_t* natoms, const double* volume,
+                       const double* energy, const double* forces, const double* stress,
+                       const double* eweight, const double* fweight, const double* vweight,
+                       const double* type_fraction, const double* blank2j, int ncfg, int numtypes,
+                       int ncoeff, int flags, double* A, int64_t lda, double* b, double* w,
+                       int32_t* nonfinite, int64_t n_rows_hint, cudaStream_t s) {
+  ScatterArgs a;
+  a.raw = raw; a.raw_row_off = raw_row_off; a.out_row_off = out_row_off; a.natoms = natoms;
+  a.volume = volume; a.energy = energy; a.forces = forces; a.stress = stress;
+  a.eweight = eweight; a.fweight = fweight; a.vweight = vweight; a.type_fraction = type_fraction;
+  a.blank2j = blank2j; a.ncfg = ncfg; a.numtypes = numtypes; a.ncoeff = ncoeff; a.flags = flags;
+  a.A = A; a.lda = lda; a.b = b; a.w = w; a.nonfinite = nonfinite;
+  // one warp per output row, grid-stride; enough CTAs for >= 8 resident per SM
+  int64_t warps_needed = n_rows_hint > 0 ? n_rows_hint : 1;
+  int64_t ctas = fsb_ceil_div(warps_needed, 8);
+  const int64_t cap = (int64_t)h->sm_count * 16;
+  if (ctas > cap) ctas = cap;
+  scatter_kernel<<<(unsigned)ctas, 256, 0, s>>>(a);
+  FSB_LAUNCH_CHECK("scatter_kernel");
+  return FSB_OK;
+}

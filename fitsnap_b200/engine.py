@@ -1,0 +1,222 @@
+"""Device engine of the linear-fit hot path: thin Python over the C-ABI.
+
+PyTorch is used ONLY as the device container (allocation, pinned staging, the stream
+handle) and for the one collective (`torch.distributed.all_reduce`, NCCL over NVLink on a
+B200 box; gloo in CPU tests of the host logic).  All arithmetic of the path runs in the
+hand-written sm_100a kernels behind `libfitsnap_b200.so`.  There is no CPU fallback.
+
+Path: a5 mask+weight -> a6/a7/a8 Gram + factor + solve (+ refinement against A)
+-> a9 predictions; a3 scatter builds A, b, w from raw LAMMPS blocks.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+@dataclass
+class Factor:
+    buf: torch.Tensor
+    info: torch.Tensor
+    k: int
+    alpha: float
+
+
+@dataclass
+class FitResult:
+    x: torch.Tensor                 # (k,) device fp64
+    gaug: torch.Tensor              # (k+1, k+1) device fp64, already all-reduced
+    info: torch.Tensor              # int32[8] device
+    last_correction: torch.Tensor | None = None   # |dx|_inf / |x|_inf of the last refinement step (device scalar)
+    launches: int = 0               # kernels of this library launched for the fit
+    extra: dict = field(default_factory=dict)
+
+    def coefficients(self):
+        return self.x.detach().cpu().numpy().astype(np.float64, copy=True)
+
+    def info_host(self):
+        return self.info.detach().cpu().numpy()
+
+
+class Engine:
+    """One engine per process / GPU (one process per GPU under torchrun)."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("fitsnap_b200.Engine needs a CUDA device (B200, sm_100a); no CPU fallback exists")
+        self.lib = _cabi.load()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        h = ctypes.c_void_p()
+        _cabi.check("fsb_create", self.lib.fsb_create(ctypes.byref(h), self.device.index))
+        self._h = h
+        n = ctypes.c_int()
+        _cabi.check("fsb_sm_count", self.lib.fsb_sm_count(self._h, ctypes.byref(n)))
+        self.sm_count = n.value
+        self._ws = {}
+        self.launch_count = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.fsb_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _workspace(self, tag, nbytes):
+        t = self._ws.get(tag)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._ws[tag] = t
+        return t
+
+    def to_device(self, arr, dtype=torch.float64, non_blocking=True):
+        """Host numpy -> device tensor through pinned memory (or pass a device tensor through)."""
+        if isinstance(arr, torch.Tensor):
+            return arr.to(device=self.device, dtype=dtype)
+        a = np.ascontiguousarray(arr)
+        t = torch.from_numpy(a)
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        try:
+            t = t.pin_memory()
+        except RuntimeError:
+            pass
+        return t.to(self.device, non_blocking=non_blocking)
+
+    @staticmethod
+    def _check_matrix(A, b, w, testing):
+        assert A.dtype == torch.float64 and A.dim() == 2 and A.stride(1) == 1, "A must be fp64 row-major"
+        n, k = A.shape
+        assert b.dtype == torch.float64 and w.dtype == torch.float64
+        assert b.numel() == n and w.numel() == n and b.is_contiguous() and w.is_contiguous()
+        if testing is not None:
+            assert testing.dtype == torch.uint8 and testing.numel() == n and testing.is_contiguous()
+        lda = A.stride(0) if n > 1 else max(k, A.stride(0))
+        return n, k, lda
+
+    # ------------------------------------------------------------------ kernels
+    def gram(self, A, b, w, testing=None):
+        n, k, lda = self._check_matrix(A, b, w, testing)
+        gaug = torch.empty((k + 1, k + 1), dtype=torch.float64, device=self.device)
+        nbytes = self.lib.fsb_gram_workspace_bytes(self._h, n, k)
+        ws = self._workspace("gram", nbytes)
+        _cabi.check("fsb_gram", self.lib.fsb_gram(self._h, _ptr(A), lda, _ptr(b), _ptr(w), _ptr(testing), n, k,
+                                                   _ptr(gaug), _ptr(ws), ws.numel(), self._stream()))
+        self.launch_count += 2
+        return gaug
+
+    def factor(self, gaug, alpha=0.0):
+        k = gaug.shape[0] - 1
+        assert gaug.is_contiguous() and gaug.dtype == torch.float64
+        nbytes = self.lib.fsb_factor_bytes(self._h, k)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        info = torch.empty(_cabi.INFO_LEN, dtype=torch.int32, device=self.device)
+        _cabi.check("fsb_factor", self.lib.fsb_factor(self._h, _ptr(gaug), k, float(alpha), _ptr(buf), nbytes,
+                                                       _ptr(info), self._stream()))
+        npanel = (k + 63) // 64
+        self.launch_count += 2 + npanel + 2 * max(npanel - 1, 0)
+        return Factor(buf, info, k, float(alpha))
+
+    def solve(self, factor, rhs, rhs_stride=1, x_in=None, out=None):
+        k = factor.k
+        x = out if out is not None else torch.empty(k, dtype=torch.float64, device=self.device)
+        _cabi.check("fsb_factor_solve",
+                    self.lib.fsb_factor_solve(self._h, _ptr(factor.buf), k, _ptr(rhs), int(rhs_stride),
+                                              factor.alpha, _ptr(x_in), _ptr(x), self._stream()))
+        self.launch_count += 1
+        return x
+
+    def residual(self, A, b, w, testing, x):
+        """g = aw^T (bw - aw x) over this rank's rows."""
+        n, k, lda = self._check_matrix(A, b, w, testing)
+        g = torch.empty(k, dtype=torch.float64, device=self.device)
+        nbytes = self.lib.fsb_residual_workspace_bytes(self._h, n, k)
+        ws = self._workspace("residual", nbytes)
+        _cabi.check("fsb_residual", self.lib.fsb_residual(self._h, _ptr(A), lda, _ptr(b), _ptr(w), _ptr(testing),
+                                                           n, k, _ptr(x), _ptr(g), _ptr(ws), ws.numel(),
+                                                           self._stream()))
+        self.launch_count += 2
+        return g
+
+    def predict(self, A, x):
+        assert A.dtype == torch.float64 and A.dim() == 2 and A.stride(1) == 1
+        n, k = A.shape
+        lda = A.stride(0) if n > 1 else max(k, A.stride(0))
+        y = torch.empty(n, dtype=torch.float64, device=self.device)
+        _cabi.check("fsb_predict", self.lib.fsb_predict(self._h, _ptr(A), lda, n, k, _ptr(x), _ptr(y), self._stream()))
+        self.launch_count += 1 if n > 0 else 0
+        return y
+
+    def scatter(self, batch, A=None, b=None, w=None, lda=None):
+        """Assemble rows of (A, b, w) from a `ConfigBatch` already on the device."""
+        k = batch.k
+        n_out = batch.n_rows_out
+        lda = int(lda or k)
+        if A is None:
+            A = torch.empty((batch.row_end, lda), dtype=torch.float64, device=self.device)[:, :k]
+            b = torch.empty(batch.row_end, dtype=torch.float64, device=self.device)
+            w = torch.empty(batch.row_end, dtype=torch.float64, device=self.device)
+        nonfinite = torch.zeros(1, dtype=torch.int32, device=self.device)
+        _cabi.check("fsb_scatter", self.lib.fsb_scatter(
+            self._h, _ptr(batch.raw), _ptr(batch.raw_row_off), _ptr(batch.out_row_off), _ptr(batch.natoms),
+            _ptr(batch.volume), _ptr(batch.energy), _ptr(batch.forces), _ptr(batch.stress),
+            _ptr(batch.eweight), _ptr(batch.fweight), _ptr(batch.vweight), _ptr(batch.type_fraction),
+            _ptr(batch.blank2j), batch.ncfg, batch.numtypes, batch.ncoeff, batch.flags,
+            _ptr(A), A.stride(0) if A.shape[0] > 1 else lda, _ptr(b), _ptr(w), n_out, _ptr(nonfinite), self._stream()))
+        self.launch_count += 1 if (n_out > 0 and batch.ncfg > 0) else 0
+        return A, b, w, nonfinite
+
+    # ------------------------------------------------------------------ the fit
+    def fit(self, A, b, w, testing=None, alpha=0.0, refine=2, group=None, diagnostics=True):
+        """Weighted least squares / ridge on this rank's row shard.
+
+        G~ = [aw|bw]^T[aw|bw] (one pass over A) -> all-reduce over `group` -> equilibrated
+        Cholesky of G + alpha I -> x; then `refine` rounds of x += (G+alpha I)^-1 (aw^T(bw - aw x) - alpha x)
+        with the residual streamed from A (one pass + one k-vector all-reduce per round).
+        Every rank ends with the same x (replicated solve).
+        """
+        import torch.distributed as dist
+        start = self.launch_count
+        gaug = self.gram(A, b, w, testing)
+        if group is not None and dist.get_world_size(group) > 1:
+            dist.all_reduce(gaug, op=dist.ReduceOp.SUM, group=group)
+        k = gaug.shape[0] - 1
+        f = self.factor(gaug, alpha)
+        x = self.solve(f, gaug[:, k], rhs_stride=k + 1)
+        last = None
+        for _ in range(int(refine)):
+            g = self.residual(A, b, w, testing, x)
+            if group is not None and dist.get_world_size(group) > 1:
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+            x_new = self.solve(f, g, x_in=x)
+            if diagnostics:
+                last = (x_new - x).abs().max() / x_new.abs().max().clamp_min(1e-300)
+            x = x_new
+        return FitResult(x=x, gaug=gaug, info=f.info, last_correction=last,
+                         launches=self.launch_count - start, extra={"factor": f})
+
+
+_default_engine = None
+
+
+def default_engine():
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine()
+    return _default_engine

@@ -1,0 +1,152 @@
+/*
+ * fitsnap_b200 -- C-ABI of the B200-native FitSNAP linear-fit hot path.
+ *
+ * Drop-in boundary for: per-configuration descriptor-row assembly into the design
+ * matrix A (+ truth b, weights w) and the weighted least-squares / ridge solve for the
+ * coefficient vector.  The reference has no FFI for this path (it is numpy/scipy/sklearn
+ * called from Python); each entry point below cites the reference Python interface it
+ * replaces (paths relative to the FitSNAP tree).  INTEGRATION.md shows the ctypes
+ * binding a FitSNAP maintainer would add.
+ *
+ * Conventions
+ *   - every function returns an fsb_status (0 = OK); nothing aborts or throws;
+ *   - all data pointers are DEVICE pointers (fp64 unless stated), owned by the caller;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and
+ *     asynchronous, no entry point synchronises the host;
+ *   - workspaces are caller-allocated; query the size with the *_workspace_bytes call;
+ *   - A is row-major with leading dimension lda >= k (doubles); rows are
+ *     configurations' energy/force/virial rows exactly as FitSNAP's
+ *     pt.shared_arrays['a'].array (calculator.py:287).
+ */
+#ifndef FITSNAP_B200_H
+#define FITSNAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fsb_context* fsb_handle_t;
+
+typedef enum {
+  FSB_OK = 0,
+  FSB_ERR_INVALID_ARGUMENT = 1,
+  FSB_ERR_CUDA = 2,            /* a CUDA runtime call / launch failed; see fsb_last_cuda_error */
+  FSB_ERR_WORKSPACE_TOO_SMALL = 3,
+  FSB_ERR_UNSUPPORTED = 4,
+  FSB_ERR_NO_DEVICE = 5
+} fsb_status;
+
+/* flags of fsb_scatter: which row families are assembled ([CALCULATOR] energy/force/stress,
+ * io/sections/calculator_sections/calculator.py:13-47) and [BISPECTRUM]/[ACE] bzeroflag. */
+enum {
+  FSB_ROWS_ENERGY = 1,
+  FSB_ROWS_FORCE = 2,
+  FSB_ROWS_STRESS = 4,
+  FSB_BZEROFLAG = 8,
+  FSB_SCRUB_NONFINITE = 16   /* numpy.nan_to_num on the raw block (lammps_pace.py:399-403) */
+};
+
+/* info[] written by fsb_factor (device int32[8]) */
+enum {
+  FSB_INFO_STATUS = 0,        /* 0 = positive definite; 1 = at least one pivot broke down */
+  FSB_INFO_FIRST_BAD_COLUMN = 1,
+  FSB_INFO_NUM_PINNED = 2,    /* all-zero columns of A pinned to coefficient 0 (lstsq min-norm) */
+  FSB_INFO_NUM_DEFICIENT = 3, /* columns dropped because their pivot fell below tolerance */
+  FSB_INFO_LEN = 8
+};
+
+int fsb_version(void);
+const char* fsb_status_string(int status);
+/* text of the last CUDA error seen by this library on the calling thread ("" if none) */
+const char* fsb_last_cuda_error(void);
+
+/* Context: binds a CUDA device, caches its SM count.  No reference counterpart
+ * (the reference's ParallelTools, parallel_tools.py:157, plays the runtime role). */
+int fsb_create(fsb_handle_t* out, int device);
+int fsb_destroy(fsb_handle_t h);
+int fsb_sm_count(fsb_handle_t h, int* sm_count);
+
+/* ---- K1: row build + scale + scatter ------------------------------------------------
+ * Replaces LammpsSnap._collect_lammps (calculators/lammps_snap.py:391-556) and
+ * LammpsPace._collect_lammps (calculators/lammps_pace.py:369-509), batched over ncfg
+ * configurations whose raw LAMMPS compute blocks are concatenated in `raw`.
+ *   raw          sum_c (1+3N_c+6) rows x (kraw+1) cols, row-major, kraw = ncoeff*numtypes;
+ *                last column = reference-potential energy/force/virial
+ *   raw_row_off  int64[ncfg+1] first raw row of each configuration
+ *   out_row_off  int64[ncfg+1] first output row of each configuration
+ *   natoms       int32[ncfg]
+ *   volume       [ncfg]  lmp.get_thermo("vol")            (lammps_snap.py:406)
+ *   energy       [ncfg]  data["Energy"]
+ *   forces       [3*sum N_c] data["Forces"].ravel() concatenated
+ *   stress       [ncfg*9] data["Stress"] 3x3 row-major; rows use entries
+ *                (0,0)(1,1)(2,2)(1,2)(0,2)(0,1)           (lammps_snap.py:541)
+ *   eweight/fweight/vweight [ncfg]                         (scrapers/scrape.py:323-353)
+ *   type_fraction [ncfg*numtypes] fraction of atoms per type (lammps_snap.py:459-462),
+ *                only read when FSB_BZEROFLAG is clear
+ *   blank2j      [k] column prefactor, k = kraw + (bzeroflag ? 0 : numtypes)
+ *   A,b,w        outputs; rows [out_row_off[0], out_row_off[ncfg]) are written
+ *   n_rows_out   out_row_off[ncfg] - out_row_off[0] (host copy; sizes the grid)
+ *   nonfinite    device int32 counter (or NULL), incremented when a NaN/Inf is met in the
+ *                raw values that were read -- the host raises the reference's ValueError
+ *                (lammps_snap.py:426-428) from it.  Must be zeroed by the caller.
+ * The raw blocks must be packed back to back: raw_row_off[c+1]-raw_row_off[c] = 1+3N_c+6.
+ */
+int fsb_scatter(fsb_handle_t h, const double* raw, const int64_t* raw_row_off,
+                const int64_t* out_row_off, const int32_t* natoms, const double* volume,
+                const double* energy, const double* forces, const double* stress,
+                const double* eweight, const double* fweight, const double* vweight,
+                const double* type_fraction, const double* blank2j, int32_t ncfg,
+                int32_t numtypes, int32_t ncoeff, int32_t flags, double* A, int64_t lda,
+                double* b, double* w, int64_t n_rows_out, int32_t* nonfinite, void* stream);
+
+/* ---- K2+K3+K4: fused mask + row weighting + Gram ------------------------------------
+ * Replaces the prologue and contraction of SVD/RIDGE/LASSO.perform_fit
+ * (solvers/svd.py:35-53, solvers/ridge.py:28-43, solvers/lasso.py:19-24) and the
+ * per-configuration accumulation of examples/library/transpose_trick/example.py:226-246.
+ *   testing  uint8[n_rows] or NULL; 1 = row excluded (pt.fitsnap_dict['Testing'])
+ *   gaug     out, (k+1)x(k+1) row-major symmetric:
+ *              [ aw^T aw   aw^T bw ]
+ *              [ bw^T aw   bw^T bw ]      aw = w[:,None]*A[train], bw = w*b[train]
+ */
+size_t fsb_gram_workspace_bytes(fsb_handle_t h, int64_t n_rows, int32_t k);
+int fsb_gram(fsb_handle_t h, const double* A, int64_t lda, const double* b, const double* w,
+             const uint8_t* testing, int64_t n_rows, int32_t k, double* gaug,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K6: factor + solve -------------------------------------------------------------
+ * Replaces scipy.linalg.lstsq(aw,bw,1e-13) as called at solvers/svd.py:54 (alpha = 0) and
+ * sklearn Ridge(alpha, fit_intercept=False).fit / Local_Ridge.fit as called at
+ * solvers/ridge.py:49-57, lib/ridge_solver/regressor.py:10-16 (alpha > 0), on the
+ * reduced system.  fsb_factor equilibrates S = D (G + alpha I) D, D = diag^-1/2, pins
+ * all-zero columns, and Cholesky-factors S into `factor`; fsb_factor_solve applies
+ *   x_out = (x_in ? x_in : 0) + D S^-1 D (rhs - alpha * (x_in ? x_in : 0)).
+ * With rhs = aw^T bw, x_in = NULL this is the normal-equation solution; with
+ * rhs = aw^T (bw - aw x) from fsb_residual it is one step of iterative refinement.
+ */
+size_t fsb_factor_bytes(fsb_handle_t h, int32_t k);
+int fsb_factor(fsb_handle_t h, const double* gaug, int32_t k, double alpha, void* factor,
+               size_t factor_bytes, int32_t* info, void* stream);
+int fsb_factor_solve(fsb_handle_t h, const void* factor, int32_t k, const double* rhs,
+                     int64_t rhs_stride, double alpha, const double* x_in, double* x_out,
+                     void* stream);
+
+/* ---- K7: residual / prediction pass --------------------------------------------------
+ * fsb_residual: g = aw^T (bw - aw x) in one streaming pass over A (refinement residual;
+ *   the reference computes `aw @ coef - bw` at solvers/ridge.py:60).
+ * fsb_predict:  y = A x for ALL rows (solvers/solver.py:377 `a @ self.fit`).
+ */
+size_t fsb_residual_workspace_bytes(fsb_handle_t h, int64_t n_rows, int32_t k);
+int fsb_residual(fsb_handle_t h, const double* A, int64_t lda, const double* b,
+                 const double* w, const uint8_t* testing, int64_t n_rows, int32_t k,
+                 const double* x, double* g, void* workspace, size_t workspace_bytes,
+                 void* stream);
+int fsb_predict(fsb_handle_t h, const double* A, int64_t lda, int64_t n_rows, int32_t k,
+                const double* x, double* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FITSNAP_B200_H */
