@@ -27,7 +27,7 @@ SIGNATURES = {
     "fsb_destroy": (c_int, [c_void_p]),
     "fsb_sm_count": (c_int, [c_void_p, POINTER(c_int)]),
     "fsb_scatter": (c_int, [c_void_p, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                            c_int32, c_int32, c_int32, c_int32, _P, c_int64, _P, _P, c_int64, _P, c_void_p]),
+                            c_int32, c_int32, c_int32, c_int32, _P, c_int64, _P, _P, c_int64, _P, _P, c_void_p]),
     "fsb_gram_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int32]),
     "fsb_gram": (c_int, [c_void_p, _P, c_int64, _P, _P, _P, c_int64, c_int32, _P, _P, c_size_t, c_void_p]),
     "fsb_factor_bytes": (c_size_t, [c_void_p, c_int32]),

@@ -61,6 +61,7 @@ class ConfigBatch:
     k: int
     row_begin: int
     row_end: int
+    row_cfg: torch.Tensor | None = None   # int32 configuration index of every output row
     h2d_bytes: int = 0
 
     @property
@@ -124,14 +125,16 @@ def pack_configs(engine, blocks, natoms, volumes, energies, forces, stresses, ew
     b2j = np.ascontiguousarray(blank2j, dtype=np.float64)
     assert b2j.shape == (k,), (b2j.shape, k)
 
+    row_cfg = np.repeat(np.arange(ncfg, dtype=np.int32), out_rows)
     up = engine.to_device
     host = dict(raw=raw, volume=np.asarray(volumes, dtype=np.float64), energy=np.asarray(energies, dtype=np.float64),
                 forces=fcat, stress=st, eweight=np.asarray(eweights, dtype=np.float64),
                 fweight=np.asarray(fweights, dtype=np.float64), vweight=np.asarray(vweights, dtype=np.float64),
                 type_fraction=tf, blank2j=b2j)
     dev = {name: up(arr) for name, arr in host.items()}
-    nbytes = sum(a.nbytes for a in host.values()) + raw_off.nbytes + out_off.nbytes + natoms.nbytes
+    nbytes = sum(a.nbytes for a in host.values()) + raw_off.nbytes + out_off.nbytes + natoms.nbytes + row_cfg.nbytes
     return ConfigBatch(raw_row_off=up(raw_off, dtype=torch.int64), out_row_off=up(out_off, dtype=torch.int64),
                        natoms=up(natoms, dtype=torch.int32), ncfg=ncfg, numtypes=int(numtypes), ncoeff=int(ncoeff),
                        flags=make_flags(energy, force, stress, bzeroflag, scrub_nonfinite), k=k,
-                       row_begin=int(out_off[0]), row_end=int(out_off[-1]), h2d_bytes=int(nbytes), **dev)
+                       row_begin=int(out_off[0]), row_end=int(out_off[-1]), row_cfg=up(row_cfg, dtype=torch.int32),
+                       h2d_bytes=int(nbytes), **dev)

@@ -24,7 +24,7 @@ int fsb_launch_scatter(const fsb_context* h, const double* raw, const int64_t* r
                        const double* eweight, const double* fweight, const double* vweight,
                        const double* type_fraction, const double* blank2j, int ncfg, int numtypes,
                        int ncoeff, int flags, double* A, int64_t lda, double* b, double* w,
-                       int32_t* nonfinite, int64_t n_rows_hint, cudaStream_t s);
+                       int32_t* nonfinite, const int32_t* row_cfg, int64_t n_rows_hint, cudaStream_t s);
 
 static thread_local char g_cuda_err[512] = "";
 
@@ -95,7 +95,7 @@ int fsb_scatter(fsb_handle_t h, const double* raw, const int64_t* raw_row_off, c
                 const double* stress, const double* eweight, const double* fweight, const double* vweight,
                 const double* type_fraction, const double* blank2j, int32_t ncfg, int32_t numtypes,
                 int32_t ncoeff, int32_t flags, double* A, int64_t lda, double* b, double* w,
-                int64_t n_rows_out, int32_t* nonfinite, void* stream) {
+                int64_t n_rows_out, const int32_t* row_cfg, int32_t* nonfinite, void* stream) {
   if (!h || ncfg < 0 || numtypes < 1 || ncoeff < 1 || n_rows_out < 0) return FSB_ERR_INVALID_ARGUMENT;
   if (ncfg == 0 || n_rows_out == 0) return FSB_OK;
   if (!raw || !raw_row_off || !out_row_off || !natoms || !blank2j || !A || !b || !w)
@@ -109,7 +109,7 @@ int fsb_scatter(fsb_handle_t h, const double* raw, const int64_t* raw_row_off, c
   if ((flags & FSB_ROWS_STRESS) && (!stress || !vweight || !volume)) return FSB_ERR_INVALID_ARGUMENT;
   return fsb_launch_scatter(h, raw, raw_row_off, out_row_off, natoms, volume, energy, forces, stress, eweight,
                             fweight, vweight, type_fraction, blank2j, ncfg, numtypes, ncoeff, flags, A, lda, b,
-                            w, nonfinite, n_rows_out, (cudaStream_t)stream);
+                            w, nonfinite, row_cfg, n_rows_out, (cudaStream_t)stream);
 }
 
 size_t fsb_gram_workspace_bytes(fsb_handle_t h, int64_t n_rows, int32_t k) {

@@ -39,7 +39,7 @@ static inline int64_t fsb_round_up(int64_t a, int64_t b) { return fsb_ceil_div(a
 // Gram: output is tiled in GT x GT super-tiles of the augmented (k+1)x(k+1) matrix; only
 // lower-triangular super-tiles are computed.
 constexpr int FSB_GT = 128;          // super-tile edge (columns of A)
-constexpr int FSB_GRCH = 16;         // rows of A staged in shared memory per pipeline step
+constexpr int FSB_GRCH = 32;         // rows of A per shared-memory pipeline stage
 constexpr int FSB_GLDS = FSB_GT + 4; // smem row pitch in doubles: == 4 (mod 16) -> conflict-free DMMA fragment loads
 constexpr int FSB_GTHREADS = 512;    // 16 warps, each owning a 32x32 sub-tile (4x4 DMMA 8x8 blocks)
 

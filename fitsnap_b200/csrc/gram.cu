@@ -7,16 +7,25 @@
 //
 // Design (B200, sm_100a):
 //   * tcgen05 has no fp64 MMA kind, so the fp64-exact contraction runs on the fp64 tensor
-//     path that does exist on sm_100a: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).
+//     sub-pipe that does exist on sm_100a: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; measured peak
+//     on this pool 37.1 TFLOP/s, tools/ubench/fp64_rates.cu).
 //   * The augmented matrix has ka = k+1 columns (column k is bw), so G, c = aw^T bw and
 //     bw^T bw come out of ONE symmetric product.  Only lower-triangular 128x128 super-tiles
 //     are computed; the final reduction mirrors them.
 //   * grid = (#lower-tri super-tiles) x (#row chunks); blockIdx is tile-fastest so the CTAs
 //     that share a row chunk run together and re-reads of A hit the 126 MB L2.
-//   * each CTA streams its row chunk through a double-buffered shared-memory stage of 16 rows;
-//     weighting / masking / the b column are applied on the way in (registers), so HBM sees
-//     A exactly once per super-tile column range and nothing else.
-//   * smem row pitch 132 doubles (== 4 mod 16) makes every DMMA fragment load conflict-free.
+//   * each CTA streams its row chunk through a 3-stage cp.async (LDGSTS) ring of 32-row stages:
+//     global -> shared memory with no register staging, zero-fill for rows/columns past the
+//     edge, one __syncthreads per stage.  lda is arbitrary (K = 31, 69, 110 ... are real
+//     FitSNAP widths), so the copies are 8-byte; TMA needs 16-byte pitches and is not used here.
+//   * row weights (0 for test rows) ride along in the stage and are applied when a DMMA
+//     fragment is read from shared memory: fl(w*a), the same rounding as the reference's aw.
+//     The multiplies run on the plain fp64 pipe, which is separate from the DMMA sub-pipe.
+//   * smem row pitch 132 doubles (== 4 mod 16) makes every fragment load conflict-free.
+//   * the 16 warp tiles (32x32 each) of a partial / diagonal super-tile carry unequal DMMA
+//     counts: they are dealt to warps by a longest-processing-time greedy so the four DMMA
+//     sub-pipes of the SM (warp % 4) stay balanced; the inner loop is specialised on the tile
+//     shape so no predicate sits between DMMAs.
 //   * split-K partials go to a workspace and are summed in a fixed order (deterministic).
 #include "fsb_common.cuh"
 
@@ -26,8 +35,7 @@ struct GramArgs {
   const double* A;
   int64_t lda;
   const double* b;
-  const double* w;
-  const uint8_t* testing;
+  const double* w;      // effective weights: 0 for rows excluded from training
   int64_t n_rows;
   int k;
   int ntile;
@@ -35,11 +43,27 @@ struct GramArgs {
   double* partial;
 };
 
+constexpr int RCH = FSB_GRCH;                    // rows per stage
+constexpr int NSTAGE = 3;
+constexpr int RANGE_DOUBLES = RCH * FSB_GLDS;    // one column range of one stage
+constexpr int STAGE_DOUBLES = 2 * RANGE_DOUBLES + RCH;   // I range, J range, weights
+constexpr int ROWS_PER_THREAD = RCH / (FSB_GTHREADS / FSB_GT);
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
+
+// 8-byte asynchronous global->shared copy; src_bytes = 0 zero-fills without touching memory.
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int nbytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(saddr), "l"(gsrc), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void tile_coords(int tile, int& ti, int& tj) {
   int t = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
@@ -49,11 +73,34 @@ __device__ __forceinline__ void tile_coords(int tile, int& ti, int& tj) {
   tj = tile - t * (t + 1) / 2;
 }
 
-constexpr int RANGE_DOUBLES = FSB_GRCH * FSB_GLDS;  // one column range of one stage
-constexpr int ROWS_PER_THREAD = FSB_GRCH / (FSB_GTHREADS / FSB_GT);  // 16 / 4 = 4
+// DMMA block of one stage for one warp tile of MI x NJ 8x8 blocks (OND: tile sits on the
+// diagonal of a diagonal super-tile: only blocks j <= i, and the B fragments are the A fragments).
+template <int MI, int NJ, bool OND>
+__device__ __forceinline__ void compute_stage(double (&acc)[4][4][2], const double* __restrict__ fI,
+                                              const double* __restrict__ fJ, const double* __restrict__ fW) {
+#pragma unroll 2
+  for (int ks = 0; ks < RCH / 4; ++ks) {
+    const double wv = fW[ks * 4];
+    double af[MI], bf[NJ];
+#pragma unroll
+    for (int i = 0; i < MI; ++i) af[i] = fI[ks * 4 * FSB_GLDS + i * 8] * wv;
+    if (OND) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) bf[j] = af[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) bf[j] = fJ[ks * 4 * FSB_GLDS + j * 8] * wv;
+    }
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if (!OND || j <= i) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+  }
+}
 
 __global__ void __launch_bounds__(FSB_GTHREADS, 1) gram_dmma_kernel(GramArgs p) {
-  extern __shared__ double smem[];  // [2 stages][2 ranges][GRCH][GLDS]
+  extern __shared__ double smem[];  // [NSTAGE][ I: RCH x GLDS | J: RCH x GLDS | w: RCH ]
 
   const int tile = blockIdx.x % p.ntile;
   const int64_t chunk = blockIdx.x / p.ntile;
@@ -67,57 +114,87 @@ __global__ void __launch_bounds__(FSB_GTHREADS, 1) gram_dmma_kernel(GramArgs p) 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int wr = warp >> 2, wc = warp & 3;  // 4x4 grid of 32x32 warp tiles
 
   int nbI = (ka - colI0 + 7) >> 3; nbI = nbI > 16 ? 16 : nbI;
   int nbJ = (ka - colJ0 + 7) >> 3; nbJ = nbJ > 16 ? 16 : nbJ;
+
+  // Deal the 16 warp tiles to warps (LPT greedy over the four schedulers, warp % 4).
+  __shared__ unsigned char s_map[16];
+  if (tid == 0) {
+    int cost[16], order[16], load[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
+    for (int t = 0; t < 16; ++t) {
+      const int r = t >> 2, c = t & 3;
+      int m = nbI - 4 * r; m = m > 4 ? 4 : (m < 0 ? 0 : m);
+      int n = nbJ - 4 * c; n = n > 4 ? 4 : (n < 0 ? 0 : n);
+      cost[t] = (diag && c > r) ? 0 : ((diag && c == r) ? m * (m + 1) / 2 : m * n);
+      order[t] = t;
+    }
+    for (int a = 1; a < 16; ++a) {  // insertion sort, descending cost
+      const int o = order[a];
+      int q = a - 1;
+      while (q >= 0 && cost[order[q]] < cost[o]) { order[q + 1] = order[q]; --q; }
+      order[q + 1] = o;
+    }
+    for (int a = 0; a < 16; ++a) {
+      int best = -1;
+      for (int q = 0; q < 4; ++q)
+        if (cnt[q] < 4 && (best < 0 || load[q] < load[best])) best = q;
+      s_map[cnt[best] * 4 + best] = (unsigned char)order[a];
+      load[best] += cost[order[a]];
+      cnt[best] += 1;
+    }
+  }
+  __syncthreads();
+  const int wt = s_map[warp];
+  const int wr = wt >> 2, wc = wt & 3;
   int mi = nbI - 4 * wr; mi = mi > 4 ? 4 : mi;
   int nj = nbJ - 4 * wc; nj = nj > 4 ? 4 : nj;
   const bool active = (mi > 0) && (nj > 0) && (!diag || wc <= wr);
   const bool on_diag = diag && (wc == wr);
+  // shape code for the specialised inner loops (warp-uniform)
+  const int shape = !active ? -1 : (on_diag ? 16 + (mi - 1) : (mi - 1) * 4 + (nj - 1));
 
   const int64_t row_begin = chunk * p.rows_per_chunk;
   int64_t row_end = row_begin + p.rows_per_chunk;
   if (row_end > p.n_rows) row_end = p.n_rows;
-  const int nsteps = row_end > row_begin ? (int)((row_end - row_begin + FSB_GRCH - 1) / FSB_GRCH) : 0;
+  const int nsteps = row_end > row_begin ? (int)((row_end - row_begin + RCH - 1) / RCH) : 0;
 
-  // staging map: thread -> one column of the super-tile, 4 rows of the stage
+  // copy map: thread -> one column of each range, rows srow + 4*i of the stage.  The source of a
+  // column is a per-thread constant: a column of A, the b vector (column k), or nothing (zero-fill).
   const int scol = tid & (FSB_GT - 1);
   const int srow = tid >> 7;  // 0..3
   const int gcI = colI0 + scol, gcJ = colJ0 + scol;
+  const double* srcI; int64_t strI; bool useI;
+  const double* srcJ; int64_t strJ; bool useJ;
+  if (gcI < k) { srcI = p.A + gcI; strI = p.lda; useI = true; }
+  else if (gcI == k) { srcI = p.b; strI = 1; useI = true; }
+  else { srcI = p.w; strI = 0; useI = false; }
+  if (diag) { srcJ = p.w; strJ = 0; useJ = false; }
+  else if (gcJ < k) { srcJ = p.A + gcJ; strJ = p.lda; useJ = true; }
+  else if (gcJ == k) { srcJ = p.b; strJ = 1; useJ = true; }
+  else { srcJ = p.w; strJ = 0; useJ = false; }
+  const int64_t last_row = p.n_rows > 0 ? p.n_rows - 1 : 0;
 
-  double pfI[ROWS_PER_THREAD], pfJ[ROWS_PER_THREAD];
-
-  auto load_stage = [&](int step) {
-    const int64_t r0 = row_begin + (int64_t)step * FSB_GRCH + srow;
+  auto issue_stage = [&](int step) {
+    if (step < nsteps) {
+      double* st = smem + (size_t)(step % NSTAGE) * STAGE_DOUBLES;
+      const int64_t r0 = row_begin + (int64_t)step * RCH;
 #pragma unroll
-    for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-      const int64_t r = r0 + 4 * i;
-      double vI = 0.0, vJ = 0.0;
-      if (r < row_end) {
-        const bool keep = p.testing ? (p.testing[r] == 0) : true;
-        if (keep) {
-          const double wv = __ldg(p.w + r);
-          if (gcI < k) vI = __ldg(p.A + r * p.lda + gcI) * wv;
-          else if (gcI == k) vI = __ldg(p.b + r) * wv;
-          if (!diag) {
-            if (gcJ < k) vJ = __ldg(p.A + r * p.lda + gcJ) * wv;
-            else if (gcJ == k) vJ = __ldg(p.b + r) * wv;
-          }
-        }
+      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+        const int lr = srow + 4 * i;
+        const int64_t r = r0 + lr;
+        const bool in = r < row_end;
+        const int64_t rc = in ? r : last_row;   // clamped: a valid address even when zero-filling
+        cp_async8(st + lr * FSB_GLDS + scol, srcI + rc * strI, in && useI);
+        if (!diag) cp_async8(st + RANGE_DOUBLES + lr * FSB_GLDS + scol, srcJ + rc * strJ, in && useJ);
       }
-      pfI[i] = vI;
-      pfJ[i] = vJ;
+      if (tid < RCH) {
+        const int64_t r = r0 + tid;
+        const bool in = r < row_end;
+        cp_async8(st + 2 * RANGE_DOUBLES + tid, p.w + (in ? r : last_row), in);
+      }
     }
-  };
-  auto store_stage = [&](int buf) {
-    double* sI = smem + buf * (2 * RANGE_DOUBLES);
-    double* sJ = sI + RANGE_DOUBLES;
-#pragma unroll
-    for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-      sI[(srow + 4 * i) * FSB_GLDS + scol] = pfI[i];
-      if (!diag) sJ[(srow + 4 * i) * FSB_GLDS + scol] = pfJ[i];
-    }
+    cp_async_commit();   // always commit (possibly empty) so the group accounting stays uniform
   };
 
   double acc[4][4][2];
@@ -126,39 +203,35 @@ __global__ void __launch_bounds__(FSB_GTHREADS, 1) gram_dmma_kernel(GramArgs p) 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  if (nsteps > 0) {
-    load_stage(0);
-    store_stage(0);
-  }
-  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < NSTAGE - 1; ++s) issue_stage(s);
 
   const int frag_off = (lane & 3) * FSB_GLDS + (lane >> 2);
   for (int s = 0; s < nsteps; ++s) {
-    const bool more = (s + 1 < nsteps);
-    if (more) load_stage(s + 1);
+    cp_async_wait<NSTAGE - 2>();   // this thread's copies of stage s have landed
+    __syncthreads();               // everyone's have, and everyone is done reading stage s-1
+    issue_stage(s + NSTAGE - 1);   // refill the buffer stage s-1 used
     if (active) {
-      const double* sI = smem + (s & 1) * (2 * RANGE_DOUBLES);
-      const double* sJ = diag ? sI : sI + RANGE_DOUBLES;
-      const double* fI = sI + frag_off + wr * 32;
-      const double* fJ = sJ + frag_off + wc * 32;
-#pragma unroll
-      for (int ks = 0; ks < FSB_GRCH / 4; ++ks) {
-        double af[4], bf[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          af[i] = fI[ks * 4 * FSB_GLDS + i * 8];
-          bf[i] = fJ[ks * 4 * FSB_GLDS + i * 8];
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (i < mi && j < nj && (!on_diag || j <= i)) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      const double* st = smem + (size_t)(s % NSTAGE) * STAGE_DOUBLES;
+      const double* fI = st + frag_off + wr * 32;
+      const double* fJ = (diag ? st : st + RANGE_DOUBLES) + frag_off + wc * 32;
+      const double* fW = st + 2 * RANGE_DOUBLES + (lane & 3);
+      switch (shape) {
+#define FSB_CASE(MI, NJ) case (MI - 1) * 4 + (NJ - 1): compute_stage<MI, NJ, false>(acc, fI, fJ, fW); break;
+        FSB_CASE(4, 4) FSB_CASE(4, 3) FSB_CASE(4, 2) FSB_CASE(4, 1)
+        FSB_CASE(3, 4) FSB_CASE(3, 3) FSB_CASE(3, 2) FSB_CASE(3, 1)
+        FSB_CASE(2, 4) FSB_CASE(2, 3) FSB_CASE(2, 2) FSB_CASE(2, 1)
+        FSB_CASE(1, 4) FSB_CASE(1, 3) FSB_CASE(1, 2) FSB_CASE(1, 1)
+#undef FSB_CASE
+        case 16: compute_stage<1, 1, true>(acc, fI, fJ, fW); break;
+        case 17: compute_stage<2, 2, true>(acc, fI, fJ, fW); break;
+        case 18: compute_stage<3, 3, true>(acc, fI, fJ, fW); break;
+        case 19: compute_stage<4, 4, true>(acc, fI, fJ, fW); break;
+        default: break;
       }
     }
-    if (more) store_stage((s + 1) & 1);
-    __syncthreads();
   }
+  cp_async_wait<0>();
 
   // split-K partial: [chunk][tile][128][128]; only entries that the reduction reads need be valid
   if (active) {
@@ -175,20 +248,40 @@ __global__ void __launch_bounds__(FSB_GTHREADS, 1) gram_dmma_kernel(GramArgs p) 
   }
 }
 
-// Deterministic split-K reduction + symmetric mirror into the (k+1)x(k+1) output.
-__global__ void gram_reduce_kernel(const double* __restrict__ partial, int nchunk, int ntile, int ka,
-                                   double* __restrict__ gaug) {
+// effective weights: w for training rows, 0 for test rows (pt.fitsnap_dict['Testing'], svd.py:35-40)
+__global__ void mask_weights_kernel(const double* __restrict__ w, const uint8_t* __restrict__ testing,
+                                    int64_t n, double* __restrict__ weff) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) weff[i] = testing[i] ? 0.0 : w[i];
+}
+
+// Deterministic split-K reduction + symmetric mirror into the (k+1)x(k+1) output.  One block
+// owns 32 columns of one row; its 8 warps each add every 8th chunk in index order and the 8 partial
+// sums are combined in a fixed order, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ partial, int nchunk,
+                                                          int ntile, int ka, double* __restrict__ gaug) {
+  __shared__ double sh[8][33];
   const int i = blockIdx.y;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ka || j > i) return;
-  const int ti = i / FSB_GT, tj = j / FSB_GT;
-  const int tile = ti * (ti + 1) / 2 + tj;
-  const size_t off = (size_t)tile * (FSB_GT * FSB_GT) + (size_t)(i % FSB_GT) * FSB_GT + (j % FSB_GT);
-  const size_t stride = (size_t)ntile * (FSB_GT * FSB_GT);
+  const int jx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + jx;
+  const bool live = (i < ka) && (j <= i);
   double s = 0.0;
-  for (int c = 0; c < nchunk; ++c) s += partial[off + (size_t)c * stride];
-  gaug[(size_t)i * ka + j] = s;
-  gaug[(size_t)j * ka + i] = s;
+  if (live) {
+    const int ti = i / FSB_GT, tj = j / FSB_GT;
+    const int tile = ti * (ti + 1) / 2 + tj;
+    const size_t off = (size_t)tile * (FSB_GT * FSB_GT) + (size_t)(i % FSB_GT) * FSB_GT + (j % FSB_GT);
+    const size_t stride = (size_t)ntile * (FSB_GT * FSB_GT);
+    for (int c = gy; c < nchunk; c += 8) s += partial[off + (size_t)c * stride];
+  }
+  sh[gy][jx] = s;
+  __syncthreads();
+  if (gy == 0 && live) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sh[q][jx];
+    gaug[(size_t)i * ka + j] = t;
+    gaug[(size_t)j * ka + i] = t;
+  }
 }
 
 struct GramPlan {
@@ -214,31 +307,39 @@ GramPlan plan_gram(const fsb_context* h, int64_t n_rows, int k) {
 
 }  // namespace
 
+static size_t partial_bytes(const GramPlan& pl) {
+  return (size_t)pl.nchunk * pl.ntile * FSB_GT * FSB_GT * sizeof(double);
+}
+
 size_t fsb_gram_ws_bytes(const fsb_context* h, int64_t n_rows, int k) {
   GramPlan pl = plan_gram(h, n_rows, k);
-  return (size_t)pl.nchunk * pl.ntile * FSB_GT * FSB_GT * sizeof(double);
+  // split-K partials + room for the masked weight vector (used only when a test mask is given)
+  return partial_bytes(pl) + (size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double);
 }
 
 int fsb_launch_gram(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* w,
                     const uint8_t* testing, int64_t n_rows, int k, double* gaug, void* ws, size_t ws_bytes,
                     cudaStream_t s) {
   GramPlan pl = plan_gram(h, n_rows, k);
-  const size_t need = (size_t)pl.nchunk * pl.ntile * FSB_GT * FSB_GT * sizeof(double);
+  const size_t need = partial_bytes(pl) + (size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double);
   if (ws_bytes < need) return FSB_ERR_WORKSPACE_TOO_SMALL;
-  GramArgs a;
-  a.A = A; a.lda = lda; a.b = b; a.w = w; a.testing = testing; a.n_rows = n_rows; a.k = k;
-  a.ntile = pl.ntile; a.rows_per_chunk = pl.rows_per_chunk; a.partial = (double*)ws;
-  const size_t smem = (size_t)2 * 2 * RANGE_DOUBLES * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    FSB_CUDA_TRY(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  const double* weff = w;
+  if (testing && n_rows > 0) {
+    double* wbuf = (double*)((char*)ws + partial_bytes(pl));
+    mask_weights_kernel<<<(unsigned)fsb_ceil_div(n_rows, 256), 256, 0, s>>>(w, testing, n_rows, wbuf);
+    FSB_LAUNCH_CHECK("mask_weights_kernel");
+    weff = wbuf;
   }
+  GramArgs a;
+  a.A = A; a.lda = lda; a.b = b; a.w = weff; a.n_rows = n_rows; a.k = k;
+  a.ntile = pl.ntile; a.rows_per_chunk = pl.rows_per_chunk; a.partial = (double*)ws;
+  const size_t smem = (size_t)NSTAGE * STAGE_DOUBLES * sizeof(double);
+  FSB_CUDA_TRY(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   gram_dmma_kernel<<<(unsigned)(pl.nchunk * pl.ntile), FSB_GTHREADS, smem, s>>>(a);
   FSB_LAUNCH_CHECK("gram_dmma_kernel");
   const int ka = k + 1;
-  dim3 rgrid((unsigned)fsb_ceil_div(ka, 128), (unsigned)ka);
-  gram_reduce_kernel<<<rgrid, 128, 0, s>>>((const double*)ws, pl.nchunk, pl.ntile, ka, gaug);
+  dim3 rgrid((unsigned)fsb_ceil_div(ka, 32), (unsigned)ka);
+  gram_reduce_kernel<<<rgrid, 256, 0, s>>>((const double*)ws, pl.nchunk, pl.ntile, ka, gaug);
   FSB_LAUNCH_CHECK("gram_reduce_kernel");
   return FSB_OK;
 }

@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(256) trsv_kernel(FactorView f, int k, const do
   const int kp = f.kp;
   double* y = sm;                 // kp
   double* blk = sm + kp;          // NB x NBP
+  __shared__ double s_flag[NB];
   const int np = kp / NB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
 
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(256) trsv_kernel(FactorView f, int k, const do
       const int r = idx / NB, c = idx % NB;
       blk[r * NBP + c] = dblk[(size_t)r * kp + c];
     }
+    if (tid < NB) s_flag[tid] = f.flag[p * NB + tid];
     __syncthreads();
     if (warp == 0) {
       double* yp = y + p * NB;
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(256) trsv_kernel(FactorView f, int k, const do
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) {
           const double v = (yp[c] - part) / blk[c * NBP + c];
-          yp[c] = (f.flag[p * NB + c] != 0.0) ? 0.0 : v;
+          yp[c] = (s_flag[c] != 0.0) ? 0.0 : v;
         }
         __syncwarp();
       }
@@ -304,6 +306,123 @@ __global__ void __launch_bounds__(256) trsv_kernel(FactorView f, int k, const do
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small systems (k <= 128, e.g. BASELINE config 2: k = 100): the whole factorisation runs in ONE CTA
+// with S resident in shared memory (pitch k|1 -> conflict-free column walks), one barrier per
+// column: the trailing update uses the unscaled column and 1/pivot, columns are scaled at the end.
+constexpr int SMALL_K = 128;
+
+__global__ void __launch_bounds__(512) small_factor_kernel(const double* __restrict__ gaug, int k, double alpha,
+                                                           FactorView f, double tol, int32_t* info) {
+  extern __shared__ double sm[];
+  const int P = k | 1;
+  double* S = sm;              // k x P
+  double* piv = sm + (size_t)k * P;   // k   (pivot, or 0 when the column was dropped)
+  double* dsc = piv + k;       // k   scales
+  const int ka = k + 1;
+  const int kp = f.kp;
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  for (int i = tid; i < k; i += nt) {
+    const double g = gaug[(size_t)i * ka + i] + alpha;
+    dsc[i] = (g > 0.0 && g < DBL_MAX) ? pow2_scale(g) : 0.0;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < k * k; idx += nt) {
+    const int i = idx / k, j = idx - i * k;
+    if (j > i) continue;
+    const double di = dsc[i], dj = dsc[j];
+    double v;
+    if (di == 0.0 || dj == 0.0) v = (i == j) ? 1.0 : 0.0;
+    else v = di * (gaug[(size_t)i * ka + j] + (i == j ? alpha : 0.0)) * dj;
+    S[i * P + j] = v;
+  }
+  __syncthreads();
+
+  const int tx = tid & 31, ty = tid >> 5, nty = nt >> 5;
+  for (int j = 0; j < k; ++j) {
+    const double pj = S[j * P + j];
+    const bool drop = !(pj > tol);
+    if (tid == 0) piv[j] = drop ? 0.0 : pj;
+    if (!drop) {
+      const double inv = 1.0 / pj;
+      for (int r = j + 1 + ty; r < k; r += nty) {       // one warp per row, lanes across columns
+        const double lrj = S[r * P + j] * inv;
+        for (int c = j + 1 + tx; c <= r; c += 32) S[r * P + c] -= lrj * S[c * P + j];
+      }
+    }
+    __syncthreads();
+  }
+
+  // scale the columns, publish the factor in the common layout (pitch kp, identity padding)
+  if (tid < FSB_INFO_LEN) info[tid] = (tid == FSB_INFO_FIRST_BAD_COLUMN) ? k : 0;
+  __syncthreads();
+  for (int idx = tid; idx < kp * kp; idx += nt) {
+    const int i = idx / kp, j = idx - i * kp;
+    double v = 0.0;
+    if (i < k && j <= i) {
+      const double pj = piv[j];
+      if (pj == 0.0) v = (i == j) ? 1.0 : 0.0;
+      else v = (i == j) ? sqrt(pj) : S[i * P + j] / sqrt(pj);
+    } else if (i == j) {
+      v = 1.0;
+    }
+    f.L[(size_t)i * kp + j] = v;
+  }
+  for (int i = tid; i < kp; i += nt) {
+    const bool real = i < k;
+    const bool dropped = real && piv[i] == 0.0 && dsc[i] != 0.0;
+    const bool pinned = real && dsc[i] == 0.0;
+    f.d[i] = (real && !dropped) ? dsc[i] : 0.0;
+    f.flag[i] = dropped ? 1.0 : 0.0;
+    if (pinned) atomicAdd(&info[FSB_INFO_NUM_PINNED], 1);
+    if (dropped) {
+      atomicAdd(&info[FSB_INFO_NUM_DEFICIENT], 1);
+      atomicExch(&info[FSB_INFO_STATUS], 1);
+      atomicMin(&info[FSB_INFO_FIRST_BAD_COLUMN], i);
+    }
+  }
+}
+
+// x_out = x_in + D L^-T L^-1 D (rhs - alpha x_in) for k <= 128: thread i owns component i, L in smem.
+__global__ void __launch_bounds__(SMALL_K) small_solve_kernel(FactorView f, int k, const double* __restrict__ rhs,
+                                                              int64_t rhs_stride, double alpha,
+                                                              const double* __restrict__ x_in,
+                                                              double* __restrict__ x_out) {
+  extern __shared__ double sm[];
+  const int P = k | 1;
+  double* L = sm;               // k x P
+  double* bc = sm + (size_t)k * P;   // broadcast slot per column
+  const int kp = f.kp;
+  const int i = threadIdx.x;
+  for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
+    const int r = idx / k, c = idx - r * k;
+    if (c <= r) L[r * P + c] = f.L[(size_t)r * kp + c];
+  }
+  double di = 0.0, xi = 0.0, y = 0.0, fl = 0.0, lii = 1.0;
+  if (i < k) {
+    di = f.d[i];
+    fl = f.flag[i];
+    xi = x_in ? x_in[i] : 0.0;
+    y = di * (rhs[(size_t)i * rhs_stride] - alpha * xi);
+  }
+  __syncthreads();
+  if (i < k) lii = 1.0 / L[i * P + i];   // reciprocal once: a double divide per column would dominate
+  // forward: L y = r (column oriented)
+  for (int j = 0; j < k; ++j) {
+    if (i == j) { y = (fl != 0.0) ? 0.0 : y * lii; bc[j] = y; }
+    __syncthreads();
+    if (i > j && i < k) y -= L[i * P + j] * bc[j];
+  }
+  // backward: L^T z = y
+  for (int j = k - 1; j >= 0; --j) {
+    if (i == j) { y = y * lii; bc[j] = y; }
+    __syncthreads();
+    if (i < j) y -= L[j * P + i] * bc[j];
+  }
+  if (i < k) x_out[i] = xi + di * y;
+}
+
 __global__ void init_info_kernel(int32_t* info, int k) {
   if (threadIdx.x < FSB_INFO_LEN) info[threadIdx.x] = (threadIdx.x == FSB_INFO_FIRST_BAD_COLUMN) ? k : 0;
 }
@@ -321,6 +440,14 @@ int fsb_launch_factor(const fsb_context* h, const double* gaug, int k, double al
   (void)h;
   if (factor_bytes < fsb_factor_bytes_impl(k)) return FSB_ERR_WORKSPACE_TOO_SMALL;
   FactorView f = view_factor(factor, k);
+  if (k <= SMALL_K) {
+    const int P = k | 1;
+    const size_t smem = ((size_t)k * P + 2 * (size_t)k) * sizeof(double);
+    FSB_CUDA_TRY(cudaFuncSetAttribute(small_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    small_factor_kernel<<<1, 512, smem, s>>>(gaug, k, alpha, f, 64.0 * (double)f.kp * DBL_EPSILON, info);
+    FSB_LAUNCH_CHECK("small_factor_kernel");
+    return FSB_OK;
+  }
   init_info_kernel<<<1, 32, 0, s>>>(info, k);
   FSB_LAUNCH_CHECK("init_info_kernel");
   equilibrate_kernel<<<f.kp, 128, 0, s>>>(gaug, k, alpha, f, info);
@@ -345,6 +472,14 @@ int fsb_launch_factor_solve(const fsb_context* h, const void* factor, int k, con
                             int64_t rhs_stride, double alpha, const double* x_in, double* x_out,
                             cudaStream_t s) {
   FactorView f = view_factor(const_cast<void*>(factor), k);
+  if (k <= SMALL_K) {
+    const int P = k | 1;
+    const size_t smem_s = ((size_t)k * P + (size_t)k) * sizeof(double);
+    FSB_CUDA_TRY(cudaFuncSetAttribute(small_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    small_solve_kernel<<<1, SMALL_K, smem_s, s>>>(f, k, rhs, rhs_stride, alpha, x_in, x_out);
+    FSB_LAUNCH_CHECK("small_solve_kernel");
+    return FSB_OK;
+  }
   const size_t smem = ((size_t)f.kp + NB * NBP) * sizeof(double);
   if (smem > h->smem_optin) return FSB_ERR_UNSUPPORTED;
   FSB_CUDA_TRY(cudaFuncSetAttribute(trsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

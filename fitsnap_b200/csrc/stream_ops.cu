@@ -8,6 +8,7 @@
 // cover HBM latency for narrow rows.  No shared-memory staging: there is no reuse.
 #include "fsb_common.cuh"
 #include <float.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -20,8 +21,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------------------ K7
-template <int NPL, int RPI, bool WITH_G>
-__global__ void __launch_bounds__(256) rowpass_kernel(const double* __restrict__ A, int64_t lda,
+template <int NPL, int RPI, bool WITH_G, int MINB>
+__global__ void __launch_bounds__(256, MINB) rowpass_kernel(const double* __restrict__ A, int64_t lda,
                                                       const double* __restrict__ b,
                                                       const double* __restrict__ w,
                                                       const uint8_t* __restrict__ testing, int64_t n_rows,
@@ -44,18 +45,29 @@ __global__ void __launch_bounds__(256) rowpass_kernel(const double* __restrict__
   for (int64_t r0 = r_begin + (int64_t)warp * RPI; r0 < r_end; r0 += (int64_t)nwarp * RPI) {
     double a[RPI][NPL];
     double wv[RPI], bv[RPI];
+    unsigned tb[RPI];
+    // all loads are unconditional (row index clamped) so none waits on another; rows past the end
+    // and test rows get weight 0 afterwards (their finite values then contribute exactly 0)
 #pragma unroll
     for (int q = 0; q < RPI; ++q) {
       const int64_t r = r0 + q;
-      bool keep = r < r_end;
-      if (WITH_G && keep && testing) keep = (testing[r] == 0);
-      wv[q] = 0.0; bv[q] = 0.0;
-      if (keep && WITH_G) { wv[q] = __ldg(w + r); bv[q] = __ldg(b + r); }
+      const int64_t rc = r < r_end ? r : r_end - 1;
+      wv[q] = 0.0; bv[q] = 0.0; tb[q] = 0u;
+      if (WITH_G) {
+        wv[q] = __ldg(w + rc);
+        bv[q] = __ldg(b + rc);
+        if (testing) tb[q] = (unsigned)__ldg(testing + rc);
+      }
 #pragma unroll
       for (int i = 0; i < NPL; ++i) {
         const int c = lane + 32 * i;
-        a[q][i] = (keep && c < k) ? __ldg(A + r * lda + c) : 0.0;
+        a[q][i] = (c < k) ? __ldg(A + rc * lda + c) : 0.0;
       }
+    }
+    if (WITH_G) {
+#pragma unroll
+      for (int q = 0; q < RPI; ++q)
+        if (r0 + q >= r_end || tb[q] != 0u) wv[q] = 0.0;
     }
 #pragma unroll
     for (int q = 0; q < RPI; ++q) {
@@ -98,13 +110,24 @@ __global__ void __launch_bounds__(256) rowpass_kernel(const double* __restrict__
   }
 }
 
-__global__ void colsum_reduce_kernel(const double* __restrict__ partial, int nparts, int k,
-                                     double* __restrict__ g) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= k) return;
+// Deterministic column sums of the per-CTA partial vectors: 32 columns x 8 part-groups per block,
+// each group adds its parts in index order, the 8 group sums are combined in a fixed order.
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const double* __restrict__ partial, int nparts, int k,
+                                                            double* __restrict__ g) {
+  __shared__ double sh[8][33];
+  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * k + c];
-  g[c] = s;
+  if (c < k)
+    for (int p = gy; p < nparts; p += 8) s += partial[(size_t)p * k + c];
+  sh[gy][cx] = s;
+  __syncthreads();
+  if (gy == 0 && c < k) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sh[q][cx];
+    g[c] = t;
+  }
 }
 
 struct RowPlan {
@@ -130,17 +153,33 @@ int launch_rowpass(const fsb_context* h, const double* A, int64_t lda, const dou
   RowPlan pl = plan_rows(h, n_rows);
   const size_t smem = WITH_G ? (size_t)k * sizeof(double) : 0;
   const int npl = (k + 31) / 32;
-#define FSB_ROWPASS(NPL, RPI)                                                                          \
-  rowpass_kernel<NPL, RPI, WITH_G><<<pl.ncta, 256, smem, s>>>(A, lda, b, w, testing, n_rows, k, x, out, \
-                                                              pl.rows_per_cta)
+  // tuning knob (read once): FSB_ROWPASS_MINB = 1|2|3 resident-CTA target of the narrow-row variants
+  static int minb = -1;
+  if (minb < 0) {
+    const char* e = getenv("FSB_ROWPASS_MINB");
+    minb = e ? atoi(e) : 2;
+    if (minb < 1 || minb > 3) minb = 2;
+  }
+#define FSB_ROWPASS_M(NPL, RPI, MINB)                                                                        \
+  rowpass_kernel<NPL, RPI, WITH_G, MINB><<<pl.ncta, 256, smem, s>>>(A, lda, b, w, testing, n_rows, k, x, out, \
+                                                                    pl.rows_per_cta)
+#define FSB_ROWPASS(NPL, RPI)                                   \
+  do {                                                          \
+    if (minb == 3) FSB_ROWPASS_M(NPL, RPI, 3);                  \
+    else if (minb == 2) FSB_ROWPASS_M(NPL, RPI, 2);             \
+    else FSB_ROWPASS_M(NPL, RPI, 1);                            \
+  } while (0)
+#define FSB_ROWPASS1(NPL, RPI) FSB_ROWPASS_M(NPL, RPI, 1)
   if (npl <= 1) FSB_ROWPASS(1, 8);
   else if (npl <= 2) FSB_ROWPASS(2, 4);
   else if (npl <= 4) FSB_ROWPASS(4, 4);
   else if (npl <= 8) FSB_ROWPASS(8, 2);
-  else if (npl <= 16) FSB_ROWPASS(16, 1);
-  else if (npl <= 32) FSB_ROWPASS(32, 1);
-  else if (npl <= 64) FSB_ROWPASS(64, 1);
+  else if (npl <= 16) FSB_ROWPASS1(16, 1);
+  else if (npl <= 32) FSB_ROWPASS1(32, 1);
+  else if (npl <= 64) FSB_ROWPASS1(64, 1);
   else return FSB_ERR_UNSUPPORTED;   // k > 2048
+#undef FSB_ROWPASS1
+#undef FSB_ROWPASS_M
 #undef FSB_ROWPASS
   FSB_LAUNCH_CHECK("rowpass_kernel");
   return FSB_OK;
@@ -167,6 +206,7 @@ struct ScatterArgs {
   double* b;
   double* w;
   int32_t* nonfinite;
+  const int32_t* row_cfg;   // optional: configuration index of every output row
 };
 
 __device__ __forceinline__ double scrub(double v, bool do_scrub, bool& bad) {
@@ -180,84 +220,140 @@ __device__ __forceinline__ double scrub(double v, bool do_scrub, bool& bad) {
   return v;
 }
 
-__global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs p) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t row0 = p.out_row_off[0];
-  const int64_t total = p.out_row_off[p.ncfg] - row0;
+// One warp handles SC_RPW consecutive output rows per iteration; the (row-independent) column map
+// raw column -> output column and the blank2J prefactors live in shared memory, so the per-element
+// work is two LDS, one LDG, at most one divide, one multiply, one STG.  All row metadata is
+// warp-uniform.  SC_RPW x SC_CU independent loads per lane are in flight before any is consumed.
+constexpr int SC_RPW = 4;
+constexpr int SC_CU = 4;
+
+struct RowMeta {
+  const double* src;   // raw row
+  double* dst;         // A row
+  double scale_div;    // energy rows: N; virial rows: V; force rows: unused
+  int kind;            // 0 energy, 1 force, 2 virial, -1 invalid
+  int cfg;
+};
+
+__global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs p, int64_t total) {
+  extern __shared__ unsigned char sc_smem[];
   const bool use_e = p.flags & FSB_ROWS_ENERGY, use_f = p.flags & FSB_ROWS_FORCE,
-             use_s = p.flags & FSB_ROWS_STRESS, bzero = p.flags & FSB_BZEROFLAG;
+             bzero = p.flags & FSB_BZEROFLAG;
   const bool do_scrub = p.flags & FSB_SCRUB_NONFINITE;
   const int kraw = p.ncoeff * p.numtypes;
   const int k = bzero ? kraw : kraw + p.numtypes;
   const int seg = p.ncoeff + 1;
   const int64_t ldr = kraw + 1;
+  double* s_b2j = reinterpret_cast<double*>(sc_smem);
+  int* s_src = reinterpret_cast<int*>(s_b2j + k);   // >= 0: raw column; < 0: lead column of type (-v-1)
+  for (int oc = threadIdx.x; oc < k; oc += blockDim.x) {
+    s_b2j[oc] = p.blank2j[oc];
+    int v = oc;
+    if (!bzero) {
+      const int t = oc / seg, q = oc - t * seg;
+      v = (q == 0) ? -(t + 1) : t * p.ncoeff + q - 1;
+    }
+    s_src[oc] = v;
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t row0 = p.out_row_off[0];
   bool bad = false;
 
-  for (int64_t rr = warp_global; rr < total; rr += nwarps) {
-    const int64_t row = row0 + rr;
-    // binary search: largest c with out_row_off[c] <= row
-    int lo = 0, hi = p.ncfg - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (p.out_row_off[mid] <= row) lo = mid; else hi = mid - 1;
-    }
-    const int c = lo;
-    int64_t local = row - p.out_row_off[c];
-    const int n = p.natoms[c];
-    const double dn = (double)n;
-    int kind;  // 0 energy, 1 force, 2 virial
-    int64_t sub;
-    if (use_e && local == 0) { kind = 0; sub = 0; }
-    else {
-      if (use_e) local -= 1;
-      if (use_f && local < 3 * (int64_t)n) { kind = 1; sub = local; }
-      else { if (use_f) local -= 3 * (int64_t)n; kind = 2; sub = local; }
-    }
-    const int64_t rraw = p.raw_row_off[c] + (kind == 0 ? 0 : (kind == 1 ? 1 + sub : 1 + 3 * (int64_t)n + sub));
-    const double* src = p.raw + rraw * ldr;
-    const double vol = p.volume[c];
-    double* dst = p.A + row * p.lda;
-
-    for (int oc = lane; oc < k; oc += 32) {
-      double v;
-      int rc = oc;
-      bool lead = false;
-      int t = 0;
-      if (!bzero) {
-        t = oc / seg;
-        const int q = oc - t * seg;
-        lead = (q == 0);
-        rc = t * p.ncoeff + q - 1;
+  for (int64_t g = warp_global; g * SC_RPW < total; g += nwarps) {
+    RowMeta m[SC_RPW];
+#pragma unroll
+    for (int q = 0; q < SC_RPW; ++q) {
+      const int64_t rr = g * SC_RPW + q;
+      m[q].kind = -1;
+      m[q].cfg = 0;
+      m[q].src = p.raw;
+      m[q].dst = p.A;
+      m[q].scale_div = 1.0;
+      if (rr < total) {
+        const int64_t row = row0 + rr;
+        int c;
+        if (p.row_cfg) {
+          c = p.row_cfg[rr];
+        } else {  // binary search: largest c with out_row_off[c] <= row
+          int lo = 0, hi = p.ncfg - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (p.out_row_off[mid] <= row) lo = mid; else hi = mid - 1;
+          }
+          c = lo;
+        }
+        int64_t local = row - p.out_row_off[c];
+        const int n = p.natoms[c];
+        int kind;
+        int64_t sub;
+        if (use_e && local == 0) { kind = 0; sub = 0; }
+        else {
+          if (use_e) local -= 1;
+          if (use_f && local < 3 * (int64_t)n) { kind = 1; sub = local; }
+          else { if (use_f) local -= 3 * (int64_t)n; kind = 2; sub = local; }
+        }
+        const int64_t rraw = p.raw_row_off[c] + (kind == 0 ? 0 : (kind == 1 ? 1 + sub : 1 + 3 * (int64_t)n + sub));
+        m[q].kind = kind;
+        m[q].cfg = c;
+        m[q].src = p.raw + rraw * ldr;
+        m[q].dst = p.A + row * p.lda;
+        m[q].scale_div = (kind == 0) ? (double)n : (kind == 2 ? p.volume[c] : 1.0);
+        if (lane == 0) {   // b and w of this row
+          const double ref = scrub(__ldg(m[q].src + kraw), do_scrub, bad);
+          double bv, wv;
+          if (kind == 0) {
+            bv = (p.energy[c] - ref) / (double)n;             // lammps_snap.py:473
+            wv = p.eweight[c];
+          } else if (kind == 1) {
+            const int64_t atom0 = (p.raw_row_off[c] - p.raw_row_off[0] - 7 * (int64_t)c) / 3;
+            bv = p.forces[3 * atom0 + sub] - ref;             // :506-507
+            wv = p.fweight[c];
+          } else {
+            const int vi[6] = {0, 1, 2, 1, 0, 0}, vj[6] = {0, 1, 2, 2, 2, 1};
+            bv = p.stress[(size_t)c * 9 + vi[sub] * 3 + vj[sub]] - ref;   // :540-541
+            wv = p.vweight[c];
+          }
+          p.b[row] = bv;
+          p.w[row] = wv;
+        }
       }
-      if (lead) {
-        v = (kind == 0) ? p.type_fraction[(size_t)c * p.numtypes + t] : 0.0;
-      } else {
-        const double rv = scrub(__ldg(src + rc), do_scrub, bad);
-        if (kind == 0) v = rv / dn;                         // lammps_snap.py:435
-        else if (kind == 1) v = rv;                         // :493
-        else v = (VIRIAL_UNIT * rv) / vol;                  // :526 (multiply first, then divide)
-      }
-      dst[oc] = v * p.blank2j[oc];                          // :466-467, :501-502, :535-536
     }
-    if (lane == 0) {
-      const double ref = scrub(__ldg(src + kraw), do_scrub, bad);
-      double bv, wv;
-      if (kind == 0) {
-        bv = (p.energy[c] - ref) / dn;                      // :473
-        wv = p.eweight[c];
-      } else if (kind == 1) {
-        const int64_t atom0 = (p.raw_row_off[c] - p.raw_row_off[0] - 7 * (int64_t)c) / 3;
-        bv = p.forces[3 * atom0 + sub] - ref;               // :506-507
-        wv = p.fweight[c];
-      } else {
-        const int vi[6] = {0, 1, 2, 1, 0, 0}, vj[6] = {0, 1, 2, 2, 2, 1};
-        bv = p.stress[(size_t)c * 9 + vi[sub] * 3 + vj[sub]] - ref;   // :540-541
-        wv = p.vweight[c];
+    for (int oc0 = 0; oc0 < k; oc0 += 32 * SC_CU) {
+      double v[SC_RPW][SC_CU];
+      int srcc[SC_CU];
+#pragma unroll
+      for (int u = 0; u < SC_CU; ++u) {
+        const int oc = oc0 + lane + 32 * u;
+        srcc[u] = (oc < k) ? s_src[oc] : -1;
       }
-      p.b[row] = bv;
-      p.w[row] = wv;
+#pragma unroll
+      for (int q = 0; q < SC_RPW; ++q)
+#pragma unroll
+        for (int u = 0; u < SC_CU; ++u)
+          v[q][u] = (srcc[u] >= 0 && m[q].kind >= 0) ? __ldg(m[q].src + srcc[u]) : 0.0;
+#pragma unroll
+      for (int q = 0; q < SC_RPW; ++q) {
+        if (m[q].kind < 0) continue;
+#pragma unroll
+        for (int u = 0; u < SC_CU; ++u) {
+          const int oc = oc0 + lane + 32 * u;
+          if (oc >= k) continue;
+          double val;
+          if (srcc[u] < 0) {
+            val = (m[q].kind == 0) ? p.type_fraction[(size_t)m[q].cfg * p.numtypes + (-srcc[u] - 1)] : 0.0;
+          } else {
+            const double rv = scrub(v[q][u], do_scrub, bad);
+            if (m[q].kind == 0) val = rv / m[q].scale_div;                      // lammps_snap.py:435
+            else if (m[q].kind == 1) val = rv;                                  // :493
+            else val = (VIRIAL_UNIT * rv) / m[q].scale_div;                     // :526 (multiply, then divide)
+          }
+          m[q].dst[oc] = val * s_b2j[oc];                                       // :466-467, :501-502, :535-536
+        }
+      }
     }
   }
   if (p.nonfinite && __any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(p.nonfinite, 1);
@@ -277,7 +373,7 @@ int fsb_launch_residual(const fsb_context* h, const double* A, int64_t lda, cons
   if (ws_bytes < (size_t)pl.ncta * k * sizeof(double)) return FSB_ERR_WORKSPACE_TOO_SMALL;
   int st = launch_rowpass<true>(h, A, lda, b, w, testing, n_rows, k, x, (double*)ws, s);
   if (st != FSB_OK) return st;
-  colsum_reduce_kernel<<<(unsigned)fsb_ceil_div(k, 128), 128, 0, s>>>((const double*)ws, pl.ncta, k, g);
+  colsum_reduce_kernel<<<(unsigned)fsb_ceil_div(k, 32), 256, 0, s>>>((const double*)ws, pl.ncta, k, g);
   FSB_LAUNCH_CHECK("colsum_reduce_kernel");
   return FSB_OK;
 }
@@ -294,19 +390,22 @@ int fsb_launch_scatter(const fsb_context* h, const double* raw, const int64_t* r
                        const double* eweight, const double* fweight, const double* vweight,
                        const double* type_fraction, const double* blank2j, int ncfg, int numtypes,
                        int ncoeff, int flags, double* A, int64_t lda, double* b, double* w,
-                       int32_t* nonfinite, int64_t n_rows_hint, cudaStream_t s) {
+                       int32_t* nonfinite, const int32_t* row_cfg, int64_t n_rows_hint, cudaStream_t s) {
   ScatterArgs a;
   a.raw = raw; a.raw_row_off = raw_row_off; a.out_row_off = out_row_off; a.natoms = natoms;
   a.volume = volume; a.energy = energy; a.forces = forces; a.stress = stress;
   a.eweight = eweight; a.fweight = fweight; a.vweight = vweight; a.type_fraction = type_fraction;
   a.blank2j = blank2j; a.ncfg = ncfg; a.numtypes = numtypes; a.ncoeff = ncoeff; a.flags = flags;
-  a.A = A; a.lda = lda; a.b = b; a.w = w; a.nonfinite = nonfinite;
-  // one warp per output row, grid-stride; enough CTAs for >= 8 resident per SM
-  int64_t warps_needed = n_rows_hint > 0 ? n_rows_hint : 1;
-  int64_t ctas = fsb_ceil_div(warps_needed, 8);
-  const int64_t cap = (int64_t)h->sm_count * 16;
+  a.A = A; a.lda = lda; a.b = b; a.w = w; a.nonfinite = nonfinite; a.row_cfg = row_cfg;
+  const bool bzero = flags & FSB_BZEROFLAG;
+  const int k = ncoeff * numtypes + (bzero ? 0 : numtypes);
+  const size_t smem = (size_t)k * (sizeof(double) + sizeof(int));
+  // one warp per SC_RPW output rows, grid-stride; up to 8 CTAs of 8 warps resident per SM
+  int64_t ctas = fsb_ceil_div(fsb_ceil_div(n_rows_hint, SC_RPW), 8);
+  const int64_t cap = (int64_t)h->sm_count * 8;
   if (ctas > cap) ctas = cap;
-  scatter_kernel<<<(unsigned)ctas, 256, 0, s>>>(a);
+  if (ctas < 1) ctas = 1;
+  scatter_kernel<<<(unsigned)ctas, 256, smem, s>>>(a, n_rows_hint);
   FSB_LAUNCH_CHECK("scatter_kernel");
   return FSB_OK;
 }

@@ -93,10 +93,13 @@ class Engine:
         t = torch.from_numpy(a)
         if t.dtype != dtype:
             t = t.to(dtype)
-        try:
-            t = t.pin_memory()
-        except RuntimeError:
-            pass
+        if not t.is_pinned():
+            # one staging copy into pinned memory; callers that care (bench e2e, the calculator
+            # plugin) hand in arrays that already live in pinned memory and skip it
+            try:
+                t = t.pin_memory()
+            except RuntimeError:
+                pass
         return t.to(self.device, non_blocking=non_blocking)
 
     @staticmethod
@@ -118,7 +121,7 @@ class Engine:
         ws = self._workspace("gram", nbytes)
         _cabi.check("fsb_gram", self.lib.fsb_gram(self._h, _ptr(A), lda, _ptr(b), _ptr(w), _ptr(testing), n, k,
                                                    _ptr(gaug), _ptr(ws), ws.numel(), self._stream()))
-        self.launch_count += 2
+        self.launch_count += 2 + (1 if (testing is not None and n > 0) else 0)
         return gaug
 
     def factor(self, gaug, alpha=0.0):
@@ -130,7 +133,7 @@ class Engine:
         _cabi.check("fsb_factor", self.lib.fsb_factor(self._h, _ptr(gaug), k, float(alpha), _ptr(buf), nbytes,
                                                        _ptr(info), self._stream()))
         npanel = (k + 63) // 64
-        self.launch_count += 2 + npanel + 2 * max(npanel - 1, 0)
+        self.launch_count += 1 if k <= 128 else 2 + npanel + 2 * max(npanel - 1, 0)
         return Factor(buf, info, k, float(alpha))
 
     def solve(self, factor, rhs, rhs_stride=1, x_in=None, out=None):
@@ -178,7 +181,7 @@ class Engine:
             _ptr(batch.volume), _ptr(batch.energy), _ptr(batch.forces), _ptr(batch.stress),
             _ptr(batch.eweight), _ptr(batch.fweight), _ptr(batch.vweight), _ptr(batch.type_fraction),
             _ptr(batch.blank2j), batch.ncfg, batch.numtypes, batch.ncoeff, batch.flags,
-            _ptr(A), A.stride(0) if A.shape[0] > 1 else lda, _ptr(b), _ptr(w), n_out, _ptr(nonfinite), self._stream()))
+            _ptr(A), A.stride(0) if A.shape[0] > 1 else lda, _ptr(b), _ptr(w), n_out, _ptr(batch.row_cfg), _ptr(nonfinite), self._stream()))
         self.launch_count += 1 if (n_out > 0 and batch.ncfg > 0) else 0
         return A, b, w, nonfinite
 
@@ -210,6 +213,20 @@ class Engine:
             x = x_new
         return FitResult(x=x, gaug=gaug, info=f.info, last_correction=last,
                          launches=self.launch_count - start, extra={"factor": f})
+
+
+    def refine_once(self, A, b, w, testing, res, group=None):
+        """One more refinement round on top of a FitResult (adaptive tail for ill-conditioned fits)."""
+        import torch.distributed as dist
+        start = self.launch_count
+        f = res.extra["factor"]
+        g = self.residual(A, b, w, testing, res.x)
+        if group is not None and dist.get_world_size(group) > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+        x_new = self.solve(f, g, x_in=res.x)
+        last = (x_new - res.x).abs().max() / x_new.abs().max().clamp_min(1e-300)
+        return FitResult(x=x_new, gaug=res.gaug, info=res.info, last_correction=last,
+                         launches=res.launches + self.launch_count - start, extra=res.extra)
 
 
 _default_engine = None

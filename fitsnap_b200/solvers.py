@@ -1,0 +1,198 @@
+"""Host-side mirror of FitSNAP's linear `Solver` plugins (SVD, RIDGE, LASSO), backed by the
+B200 engine.  Same class names, constructor and `perform_fit` signatures, same infile keys,
+same result convention as the reference:
+
+    fitsnap3lib/solvers/svd.py:13-54     class SVD(Solver).perform_fit(a, b, w, fs_dict, trainall)
+    fitsnap3lib/solvers/ridge.py:6-60    class RIDGE(Solver).perform_fit(...)   [RIDGE] alpha, local_solver
+    fitsnap3lib/solvers/lasso.py:9-30    class LASSO(Solver).perform_fit()      [LASSO] alpha, max_iter
+    fitsnap3lib/solvers/solver.py:19-46  Solver.__init__(name, pt, config, linear=True), fit_gather()
+
+The classes here do NOT import fitsnap3lib (it is absent on a bare GPU box); they duck-type
+`pt` (attributes `_rank`, `shared_arrays[...].array`, `fitsnap_dict`) and `config`
+(`config.sections[...]`).  `fitsnap_b200.plugin.register()` grafts them under the reference's
+`Solver` base so that `[SOLVER] solver = SVD|RIDGE|LASSO` resolves to them through the
+reference's own factory (solvers/solver_factory.py:18-34).
+
+Inputs are host numpy fp64 (as in the reference) or CUDA tensors (device-resident shards);
+`self.fit` is a host `np.ndarray float64 (K,)` on rank 0 exactly as the reference leaves it.
+There is no CPU fallback: without the CUDA extension these classes raise.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import engine as _engine
+
+
+def _section(config, name):
+    secs = getattr(config, "sections", None)
+    if secs is None or name not in secs:
+        return None
+    return secs[name]
+
+
+def _get(sec, key, default):
+    if sec is None:
+        return default
+    if isinstance(sec, dict):
+        return sec.get(key, default)
+    return getattr(sec, key, default)
+
+
+class LinearSolverBase:
+    """Common prologue of the three linear solvers (svd.py:31-46 == ridge.py:24-39 == lasso.py:19-21)."""
+
+    #: refinement rounds: "auto" iterates until the correction stalls (one host sync per round)
+    refine = "auto"
+    max_refine = 10
+
+    def __init__(self, name, pt, config, linear=True):
+        self.name = name
+        self.pt = pt
+        self.config = config
+        self.fit = None
+        self.linear = linear
+        self.errors = []
+        self.engine = None
+        self.last_result = None
+        self.process_group = None      # set by fitsnap_b200.distributed for row-sharded fits
+
+    # -- reference API -----------------------------------------------------------------
+    def fit_gather(self):
+        """solver.py:46 (no-op in the reference too)."""
+
+    def _alpha(self):
+        return 0.0
+
+    def _training_mask(self, n, fs_dict, trainall):
+        """svd.py:35-40: fs_dict['Testing'], else trainall, else pt.fitsnap_dict['Testing'].
+        Unlike the explicit-array branch of svd.py:46 (which forgets to mask `w` and therefore
+        raises a broadcast error as soon as a test row exists) the mask is applied to a, b AND w,
+        which is what the shared-array branch svd.py:42-44 does."""
+        if fs_dict is not None:
+            testing = np.asarray(fs_dict["Testing"], dtype=bool)
+        elif trainall:
+            return None
+        else:
+            testing = np.asarray(self.pt.fitsnap_dict["Testing"], dtype=bool)
+        if testing.shape[0] != n:
+            raise ValueError("Testing mask has %d entries for %d rows" % (testing.shape[0], n))
+        return testing if testing.any() else None
+
+    def _resolve_inputs(self, a, b, w, fs_dict, trainall):
+        if a is None and b is None and w is None:          # svd.py:42-44
+            a = self.pt.shared_arrays["a"].array
+            b = self.pt.shared_arrays["b"].array
+            w = self.pt.shared_arrays["w"].array
+        if a is None or b is None or w is None:
+            raise ValueError("a, b and w must be given together")
+        n = a.shape[0]
+        if isinstance(a, np.ndarray) and a.ndim == 1:      # StubsArray of width 1 (parallel_tools.py:1067)
+            a = a.reshape(n, 1)
+        return a, b, w, self._training_mask(n, fs_dict, trainall)
+
+    def _engine(self):
+        if self.engine is None:
+            self.engine = _engine.default_engine()
+        return self.engine
+
+    def _to_device(self, a, b, w, testing):
+        eng = self._engine()
+        A = eng.to_device(a)
+        B = eng.to_device(b).reshape(-1)
+        W = eng.to_device(w).reshape(-1)
+        T = None
+        if testing is not None:
+            T = eng.to_device(np.ascontiguousarray(testing, dtype=np.uint8), dtype=torch.uint8) \
+                if not isinstance(testing, torch.Tensor) else testing.to(eng.device, torch.uint8)
+        return A, B, W, T
+
+    def _run_fit(self, A, B, W, T, alpha):
+        eng = self._engine()
+        if self.refine == "auto":
+            res = eng.fit(A, B, W, T, alpha=alpha, refine=2, group=self.process_group, diagnostics=True)
+            # adaptive tail: keep refining while the correction still shrinks (ill-conditioned systems)
+            last = float(res.last_correction) if res.last_correction is not None else 0.0
+            rounds = 2
+            while last > 1e-14 and rounds < self.max_refine:
+                res2 = eng.refine_once(A, B, W, T, res, group=self.process_group)
+                new = float(res2.last_correction)
+                res = res2
+                rounds += 1
+                if new > 0.5 * last:        # stalled at the attainable accuracy
+                    break
+                last = new
+            res.extra["refine_rounds"] = rounds
+            return res
+        return eng.fit(A, B, W, T, alpha=alpha, refine=int(self.refine), group=self.process_group,
+                       diagnostics=False)
+
+    def perform_fit(self, a=None, b=None, w=None, fs_dict=None, trainall=False):
+        """Signature and result convention of svd.py:18 / ridge.py:11: `self.fit` <- np.float64 (K,)
+        on rank 0; nothing is returned."""
+        pt = self.pt
+        sharded = self.process_group is not None
+        if getattr(pt, "_rank", 0) != 0 and not sharded:      # svd.py:33: only rank 0 fits
+            return
+        a, b, w, testing = self._resolve_inputs(a, b, w, fs_dict, trainall)
+        A, B, W, T = self._to_device(a, b, w, testing)
+        res = self._run_fit(A, B, W, T, self._alpha())
+        self.last_result = res
+        self._check_info(res)
+        self.fit = res.coefficients()
+
+    def _check_info(self, res):
+        info = res.info_host()
+        self.info = {"status": int(info[0]), "first_bad_column": int(info[1]), "pinned": int(info[2]),
+                     "deficient": int(info[3])}
+
+
+class SVD(LinearSolverBase):
+    """Drop-in for fitsnap3lib.solvers.svd.SVD: minimum of |aw x - bw| (scipy.linalg.lstsq(aw, bw,
+    1e-13) in the reference, svd.py:54).  `[EXTRAS] apply_transpose` (svd.py:48-53) asks the
+    reference to solve the same problem through aw^T aw -- which is what this path always does --
+    so it changes nothing here."""
+
+    def __init__(self, name, pt, config):
+        super().__init__(name, pt, config)
+
+
+class RIDGE(LinearSolverBase):
+    """Drop-in for fitsnap3lib.solvers.ridge.RIDGE: (aw^T aw + alpha I) x = aw^T bw with
+    alpha = [RIDGE] alpha (solver_sections/ridge.py:13).  `local_solver` selects between two
+    implementations of the same formula in the reference (sklearn vs regressor.py:10-16); both
+    map to the same device solve."""
+
+    def __init__(self, name, pt, config):
+        super().__init__(name, pt, config)
+
+    def _alpha(self):
+        sec = _section(self.config, "RIDGE")
+        return float(_get(sec, "alpha", 1.0e-8))
+
+    def perform_fit(self, a=None, b=None, w=None, fs_dict=None, trainall=False):
+        extras = _section(self.config, "EXTRAS")
+        if _get(extras, "apply_transpose", False):
+            # ridge.py:41-43 + sklearn Ridge.fit(aw^T aw, aw^T bw): ridge on the NORMAL matrix,
+            # (C^T C + alpha I) x = C^T d with C = aw^T aw, d = aw^T bw (SURVEY 3.3 semantic trap).
+            pt = self.pt
+            if getattr(pt, "_rank", 0) != 0 and self.process_group is None:
+                return
+            a, b, w, testing = self._resolve_inputs(a, b, w, fs_dict, trainall)
+            A, B, W, T = self._to_device(a, b, w, testing)
+            eng = self._engine()
+            gaug = eng.gram(A, B, W, T)
+            if self.process_group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(gaug, group=self.process_group)
+            k = gaug.shape[0] - 1
+            C = gaug[:k, :k].contiguous()
+            d = gaug[:k, k].contiguous()
+            ones = torch.ones(k, dtype=torch.float64, device=eng.device)
+            res = eng.fit(C, d, ones, None, alpha=self._alpha(), refine=2, diagnostics=False)
+            self.last_result = res
+            self._check_info(res)
+            self.fit = res.coefficients()
+            return
+        super().perform_fit(a, b, w, fs_dict, trainall)

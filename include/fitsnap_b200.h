@@ -89,6 +89,8 @@ int fsb_sm_count(fsb_handle_t h, int* sm_count);
  *   blank2j      [k] column prefactor, k = kraw + (bzeroflag ? 0 : numtypes)
  *   A,b,w        outputs; rows [out_row_off[0], out_row_off[ncfg]) are written
  *   n_rows_out   out_row_off[ncfg] - out_row_off[0] (host copy; sizes the grid)
+ *   row_cfg      int32[n_rows_out] configuration index of every output row, or NULL (the kernel
+ *                then binary-searches out_row_off per row; slower)
  *   nonfinite    device int32 counter (or NULL), incremented when a NaN/Inf is met in the
  *                raw values that were read -- the host raises the reference's ValueError
  *                (lammps_snap.py:426-428) from it.  Must be zeroed by the caller.
@@ -100,7 +102,8 @@ int fsb_scatter(fsb_handle_t h, const double* raw, const int64_t* raw_row_off,
                 const double* eweight, const double* fweight, const double* vweight,
                 const double* type_fraction, const double* blank2j, int32_t ncfg,
                 int32_t numtypes, int32_t ncoeff, int32_t flags, double* A, int64_t lda,
-                double* b, double* w, int64_t n_rows_out, int32_t* nonfinite, void* stream);
+                double* b, double* w, int64_t n_rows_out, const int32_t* row_cfg, int32_t* nonfinite,
+                void* stream);
 
 /* ---- K2+K3+K4: fused mask + row weighting + Gram ------------------------------------
  * Replaces the prologue and contraction of SVD/RIDGE/LASSO.perform_fit
