@@ -47,7 +47,6 @@ constexpr int RCH = FSB_GRCH;                    // rows per stage
 constexpr int NSTAGE = 3;
 constexpr int RANGE_DOUBLES = RCH * FSB_GLDS;    // one column range of one stage
 constexpr int STAGE_DOUBLES = 2 * RANGE_DOUBLES + RCH;   // I range, J range, weights
-constexpr int ROWS_PER_THREAD = RCH / (FSB_GTHREADS / FSB_GT);
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -60,6 +59,11 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, 
   const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
   const int nbytes = valid ? 8 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(saddr), "l"(gsrc), "r"(nbytes) : "memory");
+}
+// 16-byte variant (both addresses 16-byte aligned)
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int nbytes) {
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gsrc), "r"(nbytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -99,6 +103,7 @@ __device__ __forceinline__ void compute_stage(double (&acc)[4][4][2], const doub
   }
 }
 
+template <bool VEC16>
 __global__ void __launch_bounds__(FSB_GTHREADS, 1) gram_dmma_kernel(GramArgs p) {
   extern __shared__ double smem[];  // [NSTAGE][ I: RCH x GLDS | J: RCH x GLDS | w: RCH ]
 
@@ -159,39 +164,100 @@ __global__ void __launch_bounds__(FSB_GTHREADS, 1) gram_dmma_kernel(GramArgs p) 
   if (row_end > p.n_rows) row_end = p.n_rows;
   const int nsteps = row_end > row_begin ? (int)((row_end - row_begin + RCH - 1) / RCH) : 0;
 
-  // copy map: thread -> one column of each range, rows srow + 4*i of the stage.  The source of a
-  // column is a per-thread constant: a column of A, the b vector (column k), or nothing (zero-fill).
-  const int scol = tid & (FSB_GT - 1);
-  const int srow = tid >> 7;  // 0..3
-  const int gcI = colI0 + scol, gcJ = colJ0 + scol;
-  const double* srcI; int64_t strI; bool useI;
-  const double* srcJ; int64_t strJ; bool useJ;
-  if (gcI < k) { srcI = p.A + gcI; strI = p.lda; useI = true; }
-  else if (gcI == k) { srcI = p.b; strI = 1; useI = true; }
-  else { srcI = p.w; strI = 0; useI = false; }
-  if (diag) { srcJ = p.w; strJ = 0; useJ = false; }
-  else if (gcJ < k) { srcJ = p.A + gcJ; strJ = p.lda; useJ = true; }
-  else if (gcJ == k) { srcJ = p.b; strJ = 1; useJ = true; }
-  else { srcJ = p.w; strJ = 0; useJ = false; }
+  // ---- copy plan ------------------------------------------------------------------------------
+  // A "slot" is what one thread copies per stage row: 8 bytes of one column (scalar plan) or 16
+  // bytes of a column pair (VEC16: lda even and A 16-byte aligned).  The source of a slot is a
+  // per-thread constant: a column of A, the b vector (column k), or nothing (zero-fill).
+  constexpr int SLOTS_PER_ROW = VEC16 ? FSB_GT / 2 : FSB_GT;
+  constexpr int ROW_GROUPS = FSB_GTHREADS / SLOTS_PER_ROW;      // 8 (VEC16) or 4
+  constexpr int COPIES = RCH / ROW_GROUPS;                      // 4 (VEC16) or 8 per range per stage
+  const int slot = tid % SLOTS_PER_ROW;
+  const int srow = tid / SLOTS_PER_ROW;
+  const int scol = VEC16 ? 2 * slot : slot;
   const int64_t last_row = p.n_rows > 0 ? p.n_rows - 1 : 0;
+
+  struct Src { const double* ptr; int64_t stride; int nbytes; };
+  auto scalar_src = [&](int gc) {
+    Src r;
+    if (gc < k) { r.ptr = p.A + gc; r.stride = p.lda; r.nbytes = 8; }
+    else if (gc == k) { r.ptr = p.b; r.stride = 1; r.nbytes = 8; }
+    else { r.ptr = p.w; r.stride = 0; r.nbytes = 0; }
+    return r;
+  };
+  // per range: mode 0 = one 16-byte copy from A, 1 = two scalar slots (pair straddles column k),
+  // 2 = scalar plan (one 8-byte slot)
+  Src sI0, sI1, sJ0, sJ1;
+  int modeI, modeJ;
+  {
+    const int gc = colI0 + scol;
+    if (VEC16) {
+      if (gc + 1 < k) { modeI = 0; sI0.ptr = p.A + gc; sI0.stride = p.lda; sI0.nbytes = 16; sI1 = sI0; }
+      else if (gc > k) { modeI = 0; sI0.ptr = p.w; sI0.stride = 0; sI0.nbytes = 0; sI1 = sI0; }
+      else { modeI = 1; sI0 = scalar_src(gc); sI1 = scalar_src(gc + 1); }
+    } else { modeI = 2; sI0 = scalar_src(gc); sI1 = sI0; }
+    const int gj = colJ0 + scol;
+    if (VEC16) {
+      if (gj + 1 < k) { modeJ = 0; sJ0.ptr = p.A + gj; sJ0.stride = p.lda; sJ0.nbytes = 16; sJ1 = sJ0; }
+      else if (gj > k) { modeJ = 0; sJ0.ptr = p.w; sJ0.stride = 0; sJ0.nbytes = 0; sJ1 = sJ0; }
+      else { modeJ = 1; sJ0 = scalar_src(gj); sJ1 = scalar_src(gj + 1); }
+    } else { modeJ = 2; sJ0 = scalar_src(gj); sJ1 = sJ0; }
+  }
+
+  auto copy_slot = [&](double* dst, const Src& s0, const Src& s1, int mode, int64_t rc, bool in) {
+    if (mode == 0) cp_async16(dst, s0.ptr + rc * s0.stride, in ? s0.nbytes : 0);
+    else {
+      cp_async8(dst, s0.ptr + rc * s0.stride, in && s0.nbytes);
+      if (mode == 1) cp_async8(dst + 1, s1.ptr + rc * s1.stride, in && s1.nbytes);
+    }
+  };
+
+  // Running source pointers: the rows a thread copies form one arithmetic progression across
+  // stages (srow, srow+RG, ..., then the same rows of the next stage), so every copy costs one
+  // 64-bit add instead of a 64-bit multiply-add plus clamps.  Stages are issued in order.
+  const double* runI = sI0.ptr + (row_begin + srow) * sI0.stride;
+  const double* runJ = sJ0.ptr + (row_begin + srow) * sJ0.stride;
+  const int64_t stepI = (int64_t)ROW_GROUPS * sI0.stride;
+  const int64_t stepJ = (int64_t)ROW_GROUPS * sJ0.stride;
+  const double* runW = p.w + row_begin + (tid < RCH ? tid : 0);
 
   auto issue_stage = [&](int step) {
     if (step < nsteps) {
       double* st = smem + (size_t)(step % NSTAGE) * STAGE_DOUBLES;
       const int64_t r0 = row_begin + (int64_t)step * RCH;
+      const bool full = (r0 + RCH <= row_end);       // every stage but the last of a chunk
+      if (full) {
 #pragma unroll
-      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-        const int lr = srow + 4 * i;
-        const int64_t r = r0 + lr;
-        const bool in = r < row_end;
-        const int64_t rc = in ? r : last_row;   // clamped: a valid address even when zero-filling
-        cp_async8(st + lr * FSB_GLDS + scol, srcI + rc * strI, in && useI);
-        if (!diag) cp_async8(st + RANGE_DOUBLES + lr * FSB_GLDS + scol, srcJ + rc * strJ, in && useJ);
-      }
-      if (tid < RCH) {
-        const int64_t r = r0 + tid;
-        const bool in = r < row_end;
-        cp_async8(st + 2 * RANGE_DOUBLES + tid, p.w + (in ? r : last_row), in);
+        for (int i = 0; i < COPIES; ++i) {
+          double* dI = st + (srow + ROW_GROUPS * i) * FSB_GLDS + scol;
+          if (modeI == 0) cp_async16(dI, runI, sI0.nbytes);
+          else if (modeI == 2) cp_async8(dI, runI, sI0.nbytes != 0);
+          else copy_slot(dI, sI0, sI1, 1, r0 + srow + ROW_GROUPS * i, true);
+          runI += stepI;
+          if (!diag) {
+            double* dJ = dI + RANGE_DOUBLES;
+            if (modeJ == 0) cp_async16(dJ, runJ, sJ0.nbytes);
+            else if (modeJ == 2) cp_async8(dJ, runJ, sJ0.nbytes != 0);
+            else copy_slot(dJ, sJ0, sJ1, 1, r0 + srow + ROW_GROUPS * i, true);
+            runJ += stepJ;
+          }
+        }
+        if (tid < RCH) cp_async8(st + 2 * RANGE_DOUBLES + tid, runW, true);
+        runW += RCH;
+      } else {   // ragged last stage of the chunk: per-row predicate, clamped addresses
+#pragma unroll
+        for (int i = 0; i < COPIES; ++i) {
+          const int lr = srow + ROW_GROUPS * i;
+          const int64_t r = r0 + lr;
+          const bool in = r < row_end;
+          const int64_t rc = in ? r : last_row;
+          copy_slot(st + lr * FSB_GLDS + scol, sI0, sI1, modeI, rc, in);
+          if (!diag) copy_slot(st + RANGE_DOUBLES + lr * FSB_GLDS + scol, sJ0, sJ1, modeJ, rc, in);
+        }
+        if (tid < RCH) {
+          const int64_t r = r0 + tid;
+          const bool in = r < row_end;
+          cp_async8(st + 2 * RANGE_DOUBLES + tid, p.w + (in ? r : last_row), in);
+        }
       }
     }
     cp_async_commit();   // always commit (possibly empty) so the group accounting stays uniform
@@ -296,7 +362,7 @@ GramPlan plan_gram(const fsb_context* h, int64_t n_rows, int k) {
   const int nt = (ka + FSB_GT - 1) / FSB_GT;
   pl.ntile = nt * (nt + 1) / 2;
   // one resident CTA per SM (512 threads x <=128 regs); several waves when tiles are heterogeneous
-  int64_t want = pl.ntile == 1 ? h->sm_count : fsb_ceil_div(4 * (int64_t)h->sm_count, pl.ntile);
+  int64_t want = pl.ntile == 1 ? h->sm_count : fsb_ceil_div(8 * (int64_t)h->sm_count, pl.ntile);
   int64_t max_chunks = fsb_ceil_div(n_rows > 0 ? n_rows : 1, 4 * FSB_GRCH);
   if (want > max_chunks) want = max_chunks;
   if (want < 1) want = 1;
@@ -334,8 +400,14 @@ int fsb_launch_gram(const fsb_context* h, const double* A, int64_t lda, const do
   a.A = A; a.lda = lda; a.b = b; a.w = weff; a.n_rows = n_rows; a.k = k;
   a.ntile = pl.ntile; a.rows_per_chunk = pl.rows_per_chunk; a.partial = (double*)ws;
   const size_t smem = (size_t)NSTAGE * STAGE_DOUBLES * sizeof(double);
-  FSB_CUDA_TRY(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gram_dmma_kernel<<<(unsigned)(pl.nchunk * pl.ntile), FSB_GTHREADS, smem, s>>>(a);
+  const bool vec16 = (lda % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  if (vec16) {
+    FSB_CUDA_TRY(cudaFuncSetAttribute(gram_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gram_dmma_kernel<true><<<(unsigned)(pl.nchunk * pl.ntile), FSB_GTHREADS, smem, s>>>(a);
+  } else {
+    FSB_CUDA_TRY(cudaFuncSetAttribute(gram_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gram_dmma_kernel<false><<<(unsigned)(pl.nchunk * pl.ntile), FSB_GTHREADS, smem, s>>>(a);
+  }
   FSB_LAUNCH_CHECK("gram_dmma_kernel");
   const int ka = k + 1;
   dim3 rgrid((unsigned)fsb_ceil_div(ka, 32), (unsigned)ka);

@@ -346,9 +346,24 @@ __global__ void __launch_bounds__(512) small_factor_kernel(const double* __restr
     if (tid == 0) piv[j] = drop ? 0.0 : pj;
     if (!drop) {
       const double inv = 1.0 / pj;
-      for (int r = j + 1 + ty; r < k; r += nty) {       // one warp per row, lanes across columns
-        const double lrj = S[r * P + j] * inv;
-        for (int c = j + 1 + tx; c <= r; c += 32) S[r * P + c] -= lrj * S[c * P + j];
+      // each lane keeps its (<= 4) column-j entries in registers; one warp per row, rows unrolled
+      // by two so the LDS -> DFMA -> STS chains of independent rows overlap
+      double lc[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int c = j + 1 + tx + 32 * m;
+        lc[m] = (c < k) ? S[c * P + j] : 0.0;
+      }
+      for (int r = j + 1 + ty; r < k; r += 2 * nty) {
+        const int r2 = r + nty;
+        const double l1 = S[r * P + j] * inv;
+        const double l2 = (r2 < k) ? S[r2 * P + j] * inv : 0.0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int c = j + 1 + tx + 32 * m;
+          if (c <= r) S[r * P + c] -= l1 * lc[m];
+          if (r2 < k && c <= r2) S[r2 * P + c] -= l2 * lc[m];
+        }
       }
     }
     __syncthreads();

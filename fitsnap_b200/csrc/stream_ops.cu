@@ -220,23 +220,23 @@ __device__ __forceinline__ double scrub(double v, bool do_scrub, bool& bad) {
   return v;
 }
 
-// One warp handles SC_RPW consecutive output rows per iteration; the (row-independent) column map
-// raw column -> output column and the blank2J prefactors live in shared memory, so the per-element
-// work is two LDS, one LDG, at most one divide, one multiply, one STG.  All row metadata is
-// warp-uniform.  SC_RPW x SC_CU independent loads per lane are in flight before any is consumed.
+// A CTA walks tiles of SC_TILE consecutive output rows.  Phase 1: one thread per row resolves the
+// row's metadata (configuration, row family, source row, divisor) with independent global loads and
+// writes b and w (coalesced); the results go to shared memory.  Phase 2: each warp streams rows,
+// SC_RPW rows x SC_CU column chunks = 16 independent 8-byte loads per lane in flight, with no global
+// dependency chain in front of them.  The row-independent column map (raw column -> output column)
+// and the blank2J prefactors also live in shared memory: per element the work is two LDS, one LDG,
+// at most one divide, one multiply, one STG.
+constexpr int SC_TILE = 128;
 constexpr int SC_RPW = 4;
 constexpr int SC_CU = 4;
 
-struct RowMeta {
-  const double* src;   // raw row
-  double* dst;         // A row
-  double scale_div;    // energy rows: N; virial rows: V; force rows: unused
-  int kind;            // 0 energy, 1 force, 2 virial, -1 invalid
-  int cfg;
-};
-
-__global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs p, int64_t total) {
+__global__ void __launch_bounds__(256, 3) scatter_kernel(ScatterArgs p, int64_t total) {
   extern __shared__ unsigned char sc_smem[];
+  __shared__ int64_t m_src[SC_TILE];     // raw row index
+  __shared__ double m_div[SC_TILE];      // N (energy rows) or V (virial rows)
+  __shared__ int m_cfg[SC_TILE];
+  __shared__ int m_kind[SC_TILE];        // 0 energy, 1 force, 2 virial
   const bool use_e = p.flags & FSB_ROWS_ENERGY, use_f = p.flags & FSB_ROWS_FORCE,
              bzero = p.flags & FSB_BZEROFLAG;
   const bool do_scrub = p.flags & FSB_SCRUB_NONFINITE;
@@ -255,103 +255,130 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs p, int64_t tot
     }
     s_src[oc] = v;
   }
-  __syncthreads();
 
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int64_t row0 = p.out_row_off[0];
+  const int64_t ntiles = (total + SC_TILE - 1) / SC_TILE;
   bool bad = false;
 
-  for (int64_t g = warp_global; g * SC_RPW < total; g += nwarps) {
-    RowMeta m[SC_RPW];
-#pragma unroll
-    for (int q = 0; q < SC_RPW; ++q) {
-      const int64_t rr = g * SC_RPW + q;
-      m[q].kind = -1;
-      m[q].cfg = 0;
-      m[q].src = p.raw;
-      m[q].dst = p.A;
-      m[q].scale_div = 1.0;
-      if (rr < total) {
-        const int64_t row = row0 + rr;
-        int c;
-        if (p.row_cfg) {
-          c = p.row_cfg[rr];
-        } else {  // binary search: largest c with out_row_off[c] <= row
-          int lo = 0, hi = p.ncfg - 1;
-          while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (p.out_row_off[mid] <= row) lo = mid; else hi = mid - 1;
-          }
-          c = lo;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();   // previous tile fully consumed (and the column map is visible)
+    const int64_t t0 = tile * SC_TILE;
+    const int nrow = (int)((total - t0) < SC_TILE ? (total - t0) : SC_TILE);
+    if (threadIdx.x < nrow) {
+      const int64_t rr = t0 + threadIdx.x;
+      const int64_t row = row0 + rr;
+      int c;
+      if (p.row_cfg) {
+        c = p.row_cfg[rr];
+      } else {  // binary search: largest c with out_row_off[c] <= row
+        int lo = 0, hi = p.ncfg - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (p.out_row_off[mid] <= row) lo = mid; else hi = mid - 1;
         }
-        int64_t local = row - p.out_row_off[c];
-        const int n = p.natoms[c];
-        int kind;
-        int64_t sub;
-        if (use_e && local == 0) { kind = 0; sub = 0; }
-        else {
-          if (use_e) local -= 1;
-          if (use_f && local < 3 * (int64_t)n) { kind = 1; sub = local; }
-          else { if (use_f) local -= 3 * (int64_t)n; kind = 2; sub = local; }
-        }
-        const int64_t rraw = p.raw_row_off[c] + (kind == 0 ? 0 : (kind == 1 ? 1 + sub : 1 + 3 * (int64_t)n + sub));
-        m[q].kind = kind;
-        m[q].cfg = c;
-        m[q].src = p.raw + rraw * ldr;
-        m[q].dst = p.A + row * p.lda;
-        m[q].scale_div = (kind == 0) ? (double)n : (kind == 2 ? p.volume[c] : 1.0);
-        if (lane == 0) {   // b and w of this row
-          const double ref = scrub(__ldg(m[q].src + kraw), do_scrub, bad);
-          double bv, wv;
-          if (kind == 0) {
-            bv = (p.energy[c] - ref) / (double)n;             // lammps_snap.py:473
-            wv = p.eweight[c];
-          } else if (kind == 1) {
-            const int64_t atom0 = (p.raw_row_off[c] - p.raw_row_off[0] - 7 * (int64_t)c) / 3;
-            bv = p.forces[3 * atom0 + sub] - ref;             // :506-507
-            wv = p.fweight[c];
-          } else {
-            const int vi[6] = {0, 1, 2, 1, 0, 0}, vj[6] = {0, 1, 2, 2, 2, 1};
-            bv = p.stress[(size_t)c * 9 + vi[sub] * 3 + vj[sub]] - ref;   // :540-541
-            wv = p.vweight[c];
-          }
-          p.b[row] = bv;
-          p.w[row] = wv;
-        }
+        c = lo;
       }
+      int64_t local = row - p.out_row_off[c];
+      const int n = p.natoms[c];
+      int kind;
+      int64_t sub;
+      if (use_e && local == 0) { kind = 0; sub = 0; }
+      else {
+        if (use_e) local -= 1;
+        if (use_f && local < 3 * (int64_t)n) { kind = 1; sub = local; }
+        else { if (use_f) local -= 3 * (int64_t)n; kind = 2; sub = local; }
+      }
+      const int64_t rraw = p.raw_row_off[c] + (kind == 0 ? 0 : (kind == 1 ? 1 + sub : 1 + 3 * (int64_t)n + sub));
+      m_src[threadIdx.x] = rraw;
+      m_cfg[threadIdx.x] = c;
+      m_kind[threadIdx.x] = kind;
+      m_div[threadIdx.x] = (kind == 0) ? (double)n : (kind == 2 ? p.volume[c] : 1.0);
+      // b and w of this row
+      const double ref = scrub(__ldg(p.raw + rraw * ldr + kraw), do_scrub, bad);
+      double bv, wv;
+      if (kind == 0) {
+        bv = (p.energy[c] - ref) / (double)n;             // lammps_snap.py:473
+        wv = p.eweight[c];
+      } else if (kind == 1) {
+        const int64_t atom0 = (p.raw_row_off[c] - p.raw_row_off[0] - 7 * (int64_t)c) / 3;
+        bv = p.forces[3 * atom0 + sub] - ref;             // :506-507
+        wv = p.fweight[c];
+      } else {
+        const int vi[6] = {0, 1, 2, 1, 0, 0}, vj[6] = {0, 1, 2, 2, 2, 1};
+        bv = p.stress[(size_t)c * 9 + vi[sub] * 3 + vj[sub]] - ref;   // :540-541
+        wv = p.vweight[c];
+      }
+      p.b[row] = bv;
+      p.w[row] = wv;
     }
-    for (int oc0 = 0; oc0 < k; oc0 += 32 * SC_CU) {
-      double v[SC_RPW][SC_CU];
-      int srcc[SC_CU];
-#pragma unroll
-      for (int u = 0; u < SC_CU; ++u) {
-        const int oc = oc0 + lane + 32 * u;
-        srcc[u] = (oc < k) ? s_src[oc] : -1;
-      }
-#pragma unroll
-      for (int q = 0; q < SC_RPW; ++q)
-#pragma unroll
-        for (int u = 0; u < SC_CU; ++u)
-          v[q][u] = (srcc[u] >= 0 && m[q].kind >= 0) ? __ldg(m[q].src + srcc[u]) : 0.0;
+    __syncthreads();
+
+    for (int lr0 = warp * SC_RPW; lr0 < nrow; lr0 += nwarp * SC_RPW) {
+      const double* src[SC_RPW];
+      double* dst[SC_RPW];
+      double dv[SC_RPW];
+      int kind[SC_RPW];
 #pragma unroll
       for (int q = 0; q < SC_RPW; ++q) {
-        if (m[q].kind < 0) continue;
+        const int lr = (lr0 + q < nrow) ? lr0 + q : lr0;   // duplicates the first row past the end (not stored)
+        src[q] = p.raw + m_src[lr] * ldr;
+        dst[q] = p.A + (row0 + t0 + lr) * p.lda;
+        dv[q] = m_div[lr];
+        kind[q] = (lr0 + q < nrow) ? m_kind[lr] : -1;
+      }
+      for (int oc0 = 0; oc0 < k; oc0 += 32 * SC_CU) {
+        double v[SC_RPW][SC_CU], pref[SC_CU];
+        int srcc[SC_CU];
 #pragma unroll
         for (int u = 0; u < SC_CU; ++u) {
           const int oc = oc0 + lane + 32 * u;
-          if (oc >= k) continue;
-          double val;
-          if (srcc[u] < 0) {
-            val = (m[q].kind == 0) ? p.type_fraction[(size_t)m[q].cfg * p.numtypes + (-srcc[u] - 1)] : 0.0;
-          } else {
-            const double rv = scrub(v[q][u], do_scrub, bad);
-            if (m[q].kind == 0) val = rv / m[q].scale_div;                      // lammps_snap.py:435
-            else if (m[q].kind == 1) val = rv;                                  // :493
-            else val = (VIRIAL_UNIT * rv) / m[q].scale_div;                     // :526 (multiply, then divide)
+          const bool live = oc < k;
+          srcc[u] = live ? s_src[oc] : -1;
+          pref[u] = live ? s_b2j[oc] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < SC_RPW; ++q)
+#pragma unroll
+          for (int u = 0; u < SC_CU; ++u) v[q][u] = (srcc[u] >= 0) ? __ldg(src[q] + srcc[u]) : 0.0;
+        // non-finite detection on the raw bits (exponent all ones), scrubbed only when asked to
+        unsigned nf = 0;
+#pragma unroll
+        for (int q = 0; q < SC_RPW; ++q)
+#pragma unroll
+          for (int u = 0; u < SC_CU; ++u)
+            nf |= ((unsigned)__double2hiint(v[q][u]) & 0x7ff00000u) == 0x7ff00000u ? 1u : 0u;
+        if (nf) {
+          bad = true;
+          if (do_scrub) {
+#pragma unroll
+            for (int q = 0; q < SC_RPW; ++q)
+#pragma unroll
+              for (int u = 0; u < SC_CU; ++u) v[q][u] = scrub(v[q][u], true, bad);
           }
-          m[q].dst[oc] = val * s_b2j[oc];                                       // :466-467, :501-502, :535-536
+        }
+#pragma unroll
+        for (int q = 0; q < SC_RPW; ++q) {
+          double* d = dst[q] + oc0 + lane;
+          if (kind[q] == 1) {                                   // force rows: A = R * blank2J   (:493-502)
+#pragma unroll
+            for (int u = 0; u < SC_CU; ++u)
+              if (oc0 + lane + 32 * u < k) d[32 * u] = v[q][u] * pref[u];   // lead columns hold v = 0
+          } else if (kind[q] == 2) {                            // virial rows: (1.6021765e6*R)/V * blank2J (:526-536)
+#pragma unroll
+            for (int u = 0; u < SC_CU; ++u)
+              if (oc0 + lane + 32 * u < k)
+                d[32 * u] = ((srcc[u] >= 0) ? (VIRIAL_UNIT * v[q][u]) / dv[q] : 0.0) * pref[u];
+          } else if (kind[q] == 0) {                            // energy row: R/N (+ type fractions) * blank2J (:435-467)
+#pragma unroll
+            for (int u = 0; u < SC_CU; ++u)
+              if (oc0 + lane + 32 * u < k) {
+                const double val = (srcc[u] >= 0)
+                                       ? v[q][u] / dv[q]
+                                       : p.type_fraction[(size_t)m_cfg[lr0 + q] * p.numtypes + (-srcc[u] - 1)];
+                d[32 * u] = val * pref[u];
+              }
+          }
         }
       }
     }
@@ -400,9 +427,9 @@ int fsb_launch_scatter(const fsb_context* h, const double* raw, const int64_t* r
   const bool bzero = flags & FSB_BZEROFLAG;
   const int k = ncoeff * numtypes + (bzero ? 0 : numtypes);
   const size_t smem = (size_t)k * (sizeof(double) + sizeof(int));
-  // one warp per SC_RPW output rows, grid-stride; up to 8 CTAs of 8 warps resident per SM
-  int64_t ctas = fsb_ceil_div(fsb_ceil_div(n_rows_hint, SC_RPW), 8);
-  const int64_t cap = (int64_t)h->sm_count * 8;
+  // tiles of SC_TILE rows, grid-stride; 3 CTAs of 8 warps resident per SM
+  int64_t ctas = fsb_ceil_div(n_rows_hint, SC_TILE);
+  const int64_t cap = (int64_t)h->sm_count * 3;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
   scatter_kernel<<<(unsigned)ctas, 256, smem, s>>>(a, n_rows_hint);

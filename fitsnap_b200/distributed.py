@@ -1,0 +1,39 @@
+"""Row-sharding of the design matrix across the GPUs of one box (one process per GPU).
+
+Mirrors the reference's data distribution: every MPI rank owns the rows of a contiguous block
+of the node-shared A (`ParallelTools.new_slice_a`, fitsnap3lib/parallel_tools.py:594-651), all
+rows of a configuration stay on one rank (`split_within_node`, parallel_tools.py:509-511), and
+the multi-node ScaLAPACK solver uses a 1-D row-block grid (lib/scalapack_solver/scalapack.py:37-54).
+Here the per-rank blocks never meet in one address space: each GPU forms the Gram of its shard
+and a single all-reduce (NCCL over NVLink) sums the (k+1)^2 doubles, after which every rank
+solves the same k x k system.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_rows(n_rows, world, rank):
+    """Contiguous, balanced [lo, hi) row range of `rank` (first n % world ranks get one extra row)."""
+    base, rem = divmod(int(n_rows), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_configs_by_rows(rows_per_config, world):
+    """Split configurations into `world` CONTIGUOUS groups with near-equal row counts (a
+    configuration is never split).  Returns an int array of world+1 config boundaries.
+    The reference deals configs round-robin by count (parallel_tools.py:466, 511); balancing by
+    rows instead keeps the per-GPU Gram work equal when atom counts vary (2..257 in the examples)."""
+    rows = np.asarray(rows_per_config, dtype=np.int64)
+    csum = np.concatenate([[0], np.cumsum(rows)])
+    total = int(csum[-1])
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        j = int(np.searchsorted(csum, target, side="left"))
+        if j > 0 and abs(csum[j - 1] - target) <= abs(csum[min(j, len(rows))] - target):
+            j -= 1
+        bounds.append(min(max(j, bounds[-1]), len(rows)))
+    bounds.append(len(rows))
+    return np.asarray(bounds, dtype=np.int64)

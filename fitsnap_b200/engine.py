@@ -187,46 +187,57 @@ class Engine:
 
     # ------------------------------------------------------------------ the fit
     def fit(self, A, b, w, testing=None, alpha=0.0, refine=2, group=None, diagnostics=True):
-        """Weighted least squares / ridge on this rank's row shard.
-
-        G~ = [aw|bw]^T[aw|bw] (one pass over A) -> all-reduce over `group` -> equilibrated
-        Cholesky of G + alpha I -> x; then `refine` rounds of x += (G+alpha I)^-1 (aw^T(bw - aw x) - alpha x)
-        with the residual streamed from A (one pass + one k-vector all-reduce per round).
-        Every rank ends with the same x (replicated solve).
-        """
-        import torch.distributed as dist
-        start = self.launch_count
-        gaug = self.gram(A, b, w, testing)
-        if group is not None and dist.get_world_size(group) > 1:
-            dist.all_reduce(gaug, op=dist.ReduceOp.SUM, group=group)
-        k = gaug.shape[0] - 1
-        f = self.factor(gaug, alpha)
-        x = self.solve(f, gaug[:, k], rhs_stride=k + 1)
-        last = None
-        for _ in range(int(refine)):
-            g = self.residual(A, b, w, testing, x)
-            if group is not None and dist.get_world_size(group) > 1:
-                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
-            x_new = self.solve(f, g, x_in=x)
-            if diagnostics:
-                last = (x_new - x).abs().max() / x_new.abs().max().clamp_min(1e-300)
-            x = x_new
-        return FitResult(x=x, gaug=gaug, info=f.info, last_correction=last,
-                         launches=self.launch_count - start, extra={"factor": f})
-
+        return fit_rows(self, A, b, w, testing, alpha=alpha, refine=refine, group=group, diagnostics=diagnostics)
 
     def refine_once(self, A, b, w, testing, res, group=None):
-        """One more refinement round on top of a FitResult (adaptive tail for ill-conditioned fits)."""
-        import torch.distributed as dist
-        start = self.launch_count
-        f = res.extra["factor"]
-        g = self.residual(A, b, w, testing, res.x)
-        if group is not None and dist.get_world_size(group) > 1:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
-        x_new = self.solve(f, g, x_in=res.x)
-        last = (x_new - res.x).abs().max() / x_new.abs().max().clamp_min(1e-300)
-        return FitResult(x=x_new, gaug=res.gaug, info=res.info, last_correction=last,
-                         launches=res.launches + self.launch_count - start, extra=res.extra)
+        return refine_rows(self, A, b, w, testing, res, group=group)
+
+
+def _all_reduce(t, group):
+    import torch.distributed as dist
+    if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+def fit_rows(engine, A, b, w, testing=None, alpha=0.0, refine=2, group=None, diagnostics=True):
+    """Weighted least squares / ridge on this rank's row shard (`engine` = `Engine`, or any object
+    with gram/factor/solve/residual -- the CPU gloo tests drive this function with a stand-in).
+
+    G~ = [aw|bw]^T[aw|bw] (one pass over A) -> ONE all-reduce of (k+1)^2 doubles over `group`
+    (mirrors comm.Allreduce of examples/library/transpose_trick/example.py:241-242) -> equilibrated
+    Cholesky of G + alpha I -> x; then `refine` rounds of
+        x += (G + alpha I)^-1 (aw^T (bw - aw x) - alpha x)
+    with the residual streamed from A (one pass + one k-vector all-reduce per round).
+    Every rank ends with the same x (replicated solve, no broadcast).
+    """
+    start = getattr(engine, "launch_count", 0)
+    gaug = engine.gram(A, b, w, testing)
+    _all_reduce(gaug, group)
+    k = gaug.shape[0] - 1
+    f = engine.factor(gaug, alpha)
+    x = engine.solve(f, gaug[:, k], rhs_stride=k + 1)
+    last = None
+    for _ in range(int(refine)):
+        g = engine.residual(A, b, w, testing, x)
+        _all_reduce(g, group)
+        x_new = engine.solve(f, g, x_in=x)
+        if diagnostics:
+            last = (x_new - x).abs().max() / x_new.abs().max().clamp_min(1e-300)
+        x = x_new
+    return FitResult(x=x, gaug=gaug, info=f.info, last_correction=last,
+                     launches=getattr(engine, "launch_count", 0) - start, extra={"factor": f})
+
+
+def refine_rows(engine, A, b, w, testing, res, group=None):
+    """One more refinement round on top of a FitResult (adaptive tail for ill-conditioned fits)."""
+    start = getattr(engine, "launch_count", 0)
+    f = res.extra["factor"]
+    g = engine.residual(A, b, w, testing, res.x)
+    _all_reduce(g, group)
+    x_new = engine.solve(f, g, x_in=res.x)
+    last = (x_new - res.x).abs().max() / x_new.abs().max().clamp_min(1e-300)
+    return FitResult(x=x_new, gaug=res.gaug, info=res.info, last_correction=last,
+                     launches=res.launches + getattr(engine, "launch_count", 0) - start, extra=res.extra)
 
 
 _default_engine = None

@@ -1,0 +1,71 @@
+"""CPU, world_size 2, gloo: the N > 1 host logic -- row sharding, ONE all-reduce of the packed
+Gram, replicated solve, all-reduced refinement residual -- gives the same coefficients as the
+single-process oracle on the full matrix.  The arithmetic is a test double (tests/fake_engine.py);
+the real kernels are covered by the -m gpu tests."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fitsnap_b200.distributed import shard_configs_by_rows, shard_rows
+from oracle import linear_fit as lf
+from tests.synth import SOLVE_CASES, synth_system
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, case, alpha, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fitsnap_b200.engine import fit_rows
+    from tests.fake_engine import OracleEngine
+    a, b, w, t = synth_system(**SOLVE_CASES[case])
+    lo, hi = shard_rows(a.shape[0], world, rank)
+    A, B, W = torch.from_numpy(a[lo:hi]), torch.from_numpy(b[lo:hi]), torch.from_numpy(w[lo:hi])
+    T = torch.from_numpy(t[lo:hi].astype(np.uint8))
+    res = fit_rows(OracleEngine(), A, B, W, T, alpha=alpha, refine=2, group=dist.group.WORLD)
+    np.save(os.path.join(out_dir, "x_%d.npy" % rank), res.x.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case,alpha", [("well", 0.0), ("ill", 0.0), ("wide", 1e-6)])
+def test_row_sharded_fit_matches_single_process(tmp_path, case, alpha):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), case, alpha, str(tmp_path)), nprocs=world, join=True)
+    xs = [np.load(tmp_path / ("x_%d.npy" % r)) for r in range(world)]
+    assert np.array_equal(xs[0], xs[1])                    # replicated solve: identical on every rank
+    a, b, w, t = synth_system(**SOLVE_CASES[case])
+    ref = lf.svd_fit(a, b, w, t) if alpha == 0.0 else lf.ridge_fit_exact(a, b, w, alpha, t)
+    assert lf.coeff_rel_err(xs[0], ref)[0] < 1e-10
+
+
+def test_shard_rows_partition():
+    for n in (0, 1, 7, 1000, 1001):
+        for world in (1, 2, 3, 8):
+            cuts = [shard_rows(n, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_configs_by_rows_balances_rows():
+    rng = np.random.default_rng(0)
+    natoms = rng.integers(1, 258, 5000)
+    rows = 7 + 3 * natoms
+    for world in (2, 4, 8):
+        bnd = shard_configs_by_rows(rows, world)
+        assert bnd[0] == 0 and bnd[-1] == len(rows) and np.all(np.diff(bnd) >= 0)
+        per = np.array([rows[bnd[i]:bnd[i + 1]].sum() for i in range(world)])
+        assert per.sum() == rows.sum()
+        assert per.max() - per.min() <= 2 * rows.max()

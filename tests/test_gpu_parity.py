@@ -263,3 +263,84 @@ def test_rank_deficient_duplicate_column_is_reported(engine):
     # still a least-squares solution: same residual norm as the min-norm one
     r_ref = np.linalg.norm(a @ lf.svd_fit(a, b, w) - b)
     assert abs(np.linalg.norm(a @ x - b) - r_ref) < 1e-9 * r_ref
+
+
+# ------------------------------------------------------------------------------- plugin mirror
+def _pt(a, b, w, testing=None):
+    from types import SimpleNamespace
+    return SimpleNamespace(_rank=0,
+                           shared_arrays={"a": SimpleNamespace(array=a), "b": SimpleNamespace(array=b),
+                                          "w": SimpleNamespace(array=w)},
+                           fitsnap_dict={"Testing": list(map(bool, testing)) if testing is not None else [False] * len(b)})
+
+
+def test_solver_mirror_svd_shared_arrays_and_explicit(ta):
+    """`SVD.perform_fit()` with no arguments reads pt.shared_arrays + pt.fitsnap_dict['Testing']
+    (svd.py:42-44); with arrays and trainall=True it fits all rows (svd.py:37-38)."""
+    from types import SimpleNamespace
+    from fitsnap_b200.solvers import SVD
+    cfg = SimpleNamespace(sections={})
+    s = SVD("SVD", _pt(ta["a"], ta["b"], ta["w"], ta["testing"]), cfg)
+    s.perform_fit()
+    assert isinstance(s.fit, np.ndarray) and s.fit.dtype == np.float64 and s.fit.shape == (31,)
+    assert lf.coeff_rel_err(s.fit, ta["ref_svd_split"])[0] < 1e-10
+    s2 = SVD("SVD", _pt(ta["a"], ta["b"], ta["w"]), cfg)
+    s2.perform_fit(a=ta["a"], b=ta["b"], w=ta["w"], trainall=True)
+    assert lf.coeff_rel_err(s2.fit, ta["ref_svd"])[0] < 1e-10
+    assert np.max(np.abs(s2.fit - ta["snapcoeff"])) < 1e-10
+    s3 = SVD("SVD", _pt(ta["a"], ta["b"], ta["w"]), cfg)          # rank != 0 does not fit (svd.py:33)
+    s3.pt._rank = 1
+    s3.perform_fit()
+    assert s3.fit is None
+
+
+def test_solver_mirror_ridge_and_apply_transpose(ta):
+    from types import SimpleNamespace
+    from fitsnap_b200.solvers import RIDGE
+    a, b, w = ta["a"], ta["b"], ta["w"]
+    cfg = SimpleNamespace(sections={"RIDGE": SimpleNamespace(alpha=1e-6, local_solver=0),
+                                    "EXTRAS": SimpleNamespace(apply_transpose=0)})
+    r = RIDGE("RIDGE", _pt(a, b, w), cfg)
+    r.perform_fit(a=a, b=b, w=w, trainall=True)
+    assert lf.coeff_rel_err(r.fit, lf.ridge_fit_exact(a, b, w, 1e-6))[0] < 1e-10
+    assert lf.coeff_rel_err(r.fit, ta["ref_ridge_1e6"])[0] < 1e-6
+    # [EXTRAS] apply_transpose = 1: the reference then runs sklearn Ridge on (aw^T aw, aw^T bw), i.e.
+    # ridge on the NORMAL matrix (ridge.py:41-43; SURVEY 3.3) -- a different minimiser, mirrored here.
+    # Squaring the Gram squares its condition number again, so this is checked on the
+    # well-conditioned synthetic system with an alpha that is visible next to the spectrum of G^2.
+    a, b, w, t = synth_system(**SOLVE_CASES["well"])
+    aw, bw = lf.weighted_system(a, b, w, t)
+    C, d = aw.T @ aw, aw.T @ bw
+    alpha = 1e-6 * np.linalg.eigvalsh(C)[-1] ** 2
+    cfg_t = SimpleNamespace(sections={"RIDGE": SimpleNamespace(alpha=alpha, local_solver=0),
+                                      "EXTRAS": SimpleNamespace(apply_transpose=1)})
+    rt = RIDGE("RIDGE", _pt(a, b, w, t), cfg_t)
+    rt.perform_fit()
+    exact = lf.ridge_fit_exact(C, d, np.ones(len(d)), alpha)
+    plain = lf.ridge_fit_exact(a, b, w, alpha, t)
+    assert lf.coeff_rel_err(rt.fit, exact)[1] < 1e-6
+    assert lf.coeff_rel_err(rt.fit, plain)[1] > 1e-3          # and it is NOT ridge on A
+
+
+def test_hard_case_needs_adaptive_refinement():
+    """cond(w*A) ~ 2e7: fixed 2 rounds are not enough; the solver classes keep refining while the
+    correction shrinks (one host sync per extra round)."""
+    from types import SimpleNamespace
+    from fitsnap_b200.solvers import SVD
+    g = load_golden("solve_hard.npz")
+    a, b, w, t = synth_system(**SOLVE_CASES["hard"])
+    s = SVD("SVD", _pt(a, b, w, t), SimpleNamespace(sections={}))
+    s.perform_fit()
+    mr, l2, _ = lf.coeff_rel_err(s.fit, g["ref_svd"])
+    assert l2 < 1e-7 and s.last_result.extra["refine_rounds"] > 2, (mr, l2, s.last_result.extra)
+
+
+def test_pipeline_fit_host_raises_on_nan(engine):
+    from fitsnap_b200.pipeline import LinearFitPipeline
+    g = load_golden("scatter_snap_b1_efs.npz")
+    raw = g["raw"].copy()
+    raw[5, 1] = np.nan
+    pipe = LinearFitPipeline(int(g["numtypes"]), int(g["ncoeff"]), True, g["blank2j"], engine=engine)
+    with pytest.raises(ValueError):
+        pipe.fit_host(raw, g["natoms"], g["volume"], g["energy"], g["forces"], g["stress"], g["eweight"],
+                      g["fweight"], g["vweight"], None)
