@@ -82,9 +82,15 @@ class LinearSolverBase:
 
     def _resolve_inputs(self, a, b, w, fs_dict, trainall):
         if a is None and b is None and w is None:          # svd.py:42-44
-            a = self.pt.shared_arrays["a"].array
-            b = self.pt.shared_arrays["b"].array
-            w = self.pt.shared_arrays["w"].array
+            dev = getattr(self.pt, "fitsnap_b200_device", None)
+            nb = self.pt.shared_arrays["b"].array.shape[0]
+            if dev is not None and dev["first_row"] == 0 and dev["n_rows"] == nb:
+                # rows assembled by the drop-in calculator are still resident on the device
+                a, b, w = dev["A"], dev["b"], dev["w"]
+            else:
+                a = self.pt.shared_arrays["a"].array
+                b = self.pt.shared_arrays["b"].array
+                w = self.pt.shared_arrays["w"].array
         if a is None or b is None or w is None:
             raise ValueError("a, b and w must be given together")
         n = a.shape[0]
@@ -111,12 +117,12 @@ class LinearSolverBase:
     def _run_fit(self, A, B, W, T, alpha):
         eng = self._engine()
         if self.refine == "auto":
-            res = eng.fit(A, B, W, T, alpha=alpha, refine=2, group=self.process_group, diagnostics=True)
+            res = _engine.fit_rows(eng, A, B, W, T, alpha=alpha, refine=2, group=self.process_group, diagnostics=True)
             # adaptive tail: keep refining while the correction still shrinks (ill-conditioned systems)
             last = float(res.last_correction) if res.last_correction is not None else 0.0
             rounds = 2
             while last > 1e-14 and rounds < self.max_refine:
-                res2 = eng.refine_once(A, B, W, T, res, group=self.process_group)
+                res2 = _engine.refine_rows(eng, A, B, W, T, res, group=self.process_group)
                 new = float(res2.last_correction)
                 res = res2
                 rounds += 1
@@ -125,8 +131,8 @@ class LinearSolverBase:
                 last = new
             res.extra["refine_rounds"] = rounds
             return res
-        return eng.fit(A, B, W, T, alpha=alpha, refine=int(self.refine), group=self.process_group,
-                       diagnostics=False)
+        return _engine.fit_rows(eng, A, B, W, T, alpha=alpha, refine=int(self.refine), group=self.process_group,
+                                diagnostics=False)
 
     def perform_fit(self, a=None, b=None, w=None, fs_dict=None, trainall=False):
         """Signature and result convention of svd.py:18 / ridge.py:11: `self.fit` <- np.float64 (K,)
@@ -190,7 +196,7 @@ class RIDGE(LinearSolverBase):
             C = gaug[:k, :k].contiguous()
             d = gaug[:k, k].contiguous()
             ones = torch.ones(k, dtype=torch.float64, device=eng.device)
-            res = eng.fit(C, d, ones, None, alpha=self._alpha(), refine=2, diagnostics=False)
+            res = _engine.fit_rows(eng, C, d, ones, None, alpha=self._alpha(), refine=2, diagnostics=False)
             self.last_result = res
             self._check_info(res)
             self.fit = res.coefficients()

@@ -92,7 +92,7 @@ def scatter_cases():
             cfgs.append(c)
             blocks.append(rng.standard_normal((1 + 3 * n + 6, nc * 2 + 1)) * 10.0 ** rng.uniform(-4, 4, (1, nc * 2 + 1)))
             vols.append(float(rng.uniform(20, 4000)))
-        a, b, w, lists, _ = rd.ref_scatter(cfgs, blocks, vols, numtypes=2, types="In P", **kw)
+        a, b, w, lists, *_ = rd.ref_scatter(cfgs, blocks, vols, numtypes=2, types="In P", **kw)
         save_scatter(tag, cfgs, blocks, vols, a, b, w, lists, nc, 2, kw["bzeroflag"], b2j, tm, kw)
 
     # ACE-shaped (LammpsPace) case: [ACE] attributes injected (SURVEY 8c ACE caveat)
@@ -114,7 +114,7 @@ def scatter_cases():
             blocks.append(rng.standard_normal((1 + 3 * n + 6, nc * nt + 1)) * 10.0 ** rng.uniform(-3, 3, (1, nc * nt + 1)))
             vols.append(float(rng.uniform(20, 4000)))
         kw = dict(bzeroflag=bz, twojmax="6 6", energy=1, force=1, stress=1)
-        a, b, w, lists, _ = rd.ref_scatter(cfgs, blocks, vols, calculator="LAMMPSPACE", ace=ace, numtypes=nt,
+        a, b, w, lists, *_ = rd.ref_scatter(cfgs, blocks, vols, calculator="LAMMPSPACE", ace=ace, numtypes=nt,
                                            types="In P", **kw)
         save_scatter(tag, cfgs, blocks, vols, a, b, w, lists, nc, nt, bz, b2j, tm, kw)
 

@@ -195,11 +195,11 @@ def make_config_dict(natoms, numtypes, rng, type_names, group="G", fname="cfg", 
     }
 
 
-def ref_scatter(configs, blocks, volumes, calculator="LAMMPSSNAP", ace=None, **ctx):
+def ref_scatter(configs, blocks, volumes, calculator="LAMMPSSNAP", ace=None, use_factory=False, context=None, **ctx):
     """Run the unmodified reference calculator (`LammpsSnap`/`LammpsPace`
     allocate_per_config -> create_a -> process_configs -> collect_distributed_lists;
     fitsnap.py:134-188) over synthetic compute blocks.  Returns (A, b, w, fitsnap_dict lists, cfg)."""
-    pt, cfg = make_reference_context(**ctx)
+    pt, cfg = context if context is not None else make_reference_context(**ctx)
     if calculator == "LAMMPSPACE":
         # SURVEY 8c ACE caveat: the [ACE] section cannot be constructed without mpi4py;
         # inject exactly the attributes lammps_pace.py reads.
@@ -207,8 +207,12 @@ def ref_scatter(configs, blocks, volumes, calculator="LAMMPSSNAP", ace=None, **c
         cfg.sections["ACE"] = SimpleNamespace(**ace)
     from fitsnap3lib.calculators.lammps_snap import LammpsSnap
     from fitsnap3lib.calculators.lammps_pace import LammpsPace
-    cls = LammpsPace if calculator == "LAMMPSPACE" else LammpsSnap
-    calc = cls(calculator, pt, cfg)
+    if use_factory:     # through calculators/calculator_factory.py (returns a registered drop-in, if any)
+        from fitsnap3lib.calculators.calculator_factory import calculator as make_calculator
+        calc = make_calculator(calculator, pt, cfg)
+    else:
+        cls = LammpsPace if calculator == "LAMMPSPACE" else LammpsSnap
+        calc = cls(calculator, pt, cfg)
     calc._prepare_lammps = lambda: calc._set_structure()   # skip compute/pair set-up strings
     if calculator == "LAMMPSPACE":
         calc._set_box = lambda: calc._set_box_helper(numtypes=ace["numtypes"])
@@ -227,4 +231,4 @@ def ref_scatter(configs, blocks, volumes, calculator="LAMMPSSNAP", ace=None, **c
     b = np.array(pt.shared_arrays["b"].array, dtype=np.float64)
     w = np.array(pt.shared_arrays["w"].array, dtype=np.float64)
     lists = {k: list(v) for k, v in pt.fitsnap_dict.items() if isinstance(v, list)}
-    return a, b, w, lists, cfg
+    return a, b, w, lists, cfg, pt, calc

@@ -17,6 +17,42 @@ class _Factor:
 
 class OracleEngine:
     launch_count = 0
+    device = torch.device("cpu")
+
+    def to_device(self, arr, dtype=torch.float64, non_blocking=True):
+        if isinstance(arr, torch.Tensor):
+            return arr.to(dtype)
+        return torch.from_numpy(np.ascontiguousarray(arr)).to(dtype)
+
+    def scatter(self, batch, A=None, b=None, w=None, lda=None):
+        """Row assembly through the oracle (lammps_snap.py:391-556 restated in oracle/linear_fit.py)."""
+        nat = batch.natoms.numpy()
+        roff = batch.raw_row_off.numpy()
+        aoff = np.concatenate([[0], np.cumsum(nat.astype(np.int64))])
+        raw = batch.raw.numpy()
+        f = batch.flags
+        cfgs = []
+        for c in range(batch.ncfg):
+            cfgs.append(dict(block=raw[roff[c]:roff[c + 1]], natoms=int(nat[c]), volume=float(batch.volume[c]),
+                             energy=float(batch.energy[c]), forces=batch.forces.numpy()[3 * aoff[c]:3 * aoff[c + 1]],
+                             stress=batch.stress.numpy()[c].reshape(3, 3), eweight=float(batch.eweight[c]),
+                             fweight=float(batch.fweight[c]), vweight=float(batch.vweight[c]),
+                             type_fraction=batch.type_fraction.numpy()[c]))
+        if f & 16:
+            for c in cfgs:
+                c["block"] = np.nan_to_num(c["block"])
+        a_, b_, w_ = lf.assemble(cfgs, batch.numtypes, batch.ncoeff, bool(f & 8), batch.blank2j.numpy(),
+                                 bool(f & 1), bool(f & 2), bool(f & 4))
+        bad = torch.tensor([int(not np.isfinite(raw).all())], dtype=torch.int32)
+        if A is None:
+            return torch.from_numpy(a_), torch.from_numpy(b_), torch.from_numpy(w_), bad
+        A[batch.row_begin:batch.row_end] = torch.from_numpy(a_)
+        b[batch.row_begin:batch.row_end] = torch.from_numpy(b_)
+        w[batch.row_begin:batch.row_end] = torch.from_numpy(w_)
+        return A, b, w, bad
+
+    def predict(self, A, x):
+        return torch.from_numpy(A.numpy() @ x.numpy())
 
     def gram(self, A, b, w, testing=None):
         a, bb, ww = A.numpy(), b.numpy(), w.numpy()

@@ -79,3 +79,23 @@ def test_solver_mask_resolution_matches_reference_rules():
     r = RIDGE("RIDGE", pt, SimpleNamespace(sections={"RIDGE": SimpleNamespace(alpha=3e-5, local_solver=0)}))
     assert r._alpha() == 3e-5
     assert RIDGE("RIDGE", pt, SimpleNamespace(sections={}))._alpha() == 1e-8      # solver_sections/ridge.py:13 default
+
+
+def test_extract_compute_array_reads_a_lammps_style_double_pointer():
+    """lammps_base.py:280-307: extract_compute(name, 0, 2) returns double**; the view must alias it."""
+    import ctypes
+    from fitsnap_b200.calculators import extract_compute_array, row_metadata
+    blk = np.arange(12, dtype=np.float64).reshape(3, 4)
+
+    class Lmp:
+        def extract_compute(self, name, style, rtype):
+            assert (name, style, rtype) == ("snap", 0, 2)
+            self._row = blk.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+            return ctypes.pointer(self._row)
+
+    view = extract_compute_array(Lmp(), "snap", (3, 4))
+    assert np.array_equal(view, blk)
+    m = row_metadata(2, [1, 2], True, True, True, "grp", "f.json", True)
+    assert m["Row_Type"] == ["Energy"] + ["Force"] * 6 + ["Stress"] * 6
+    assert m["Atom_I"] == [0, 0, 0, 0, 1, 1, 1] + [0] * 6 and m["Atom_Type"] == [0, 1, 1, 1, 2, 2, 2] + [0] * 6
+    assert m["Testing"] == [True] * 13 and m["Groups"] == ["grp"] * 13

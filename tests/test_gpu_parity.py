@@ -344,3 +344,29 @@ def test_pipeline_fit_host_raises_on_nan(engine):
     with pytest.raises(ValueError):
         pipe.fit_host(raw, g["natoms"], g["volume"], g["energy"], g["forces"], g["stress"], g["eweight"],
                       g["fweight"], g["vweight"], None)
+
+
+@pytest.mark.parametrize("tag", ["snap_b0_efs", "pace_b1_efs"])
+def test_block_collector_stages_and_flushes(engine, tag):
+    """The calculator mirror's staging path (per-configuration `add`, one `flush`) gives the rows the
+    unmodified reference calculators produced, bit for bit."""
+    from fitsnap_b200.calculators import BlockCollector
+    g = load_golden("scatter_%s.npz" % tag)
+    nat = g["natoms"]
+    nt, nc, bz = int(g["numtypes"]), int(g["ncoeff"]), int(g["bzeroflag"])
+    roff = np.concatenate([[0], np.cumsum(7 + 3 * nat.astype(np.int64))])
+    aoff = np.concatenate([[0], np.cumsum(nat.astype(np.int64))])
+    tm = {"In": 1, "P": 2}
+    col = BlockCollector(engine, nt, nc, bz, g["blank2j"], tm, int(g["use_energy"]), int(g["use_force"]),
+                         int(g["use_stress"]), scrub_nonfinite=tag.startswith("pace"), capacity_rows=8)
+    for c in range(len(nat)):
+        # atom types reproducing the stored type fractions
+        counts = np.rint(g["type_fraction"][c] * nat[c]).astype(int)
+        types = ["In"] * counts[0] + ["P"] * counts[1]
+        col.add(g["raw"][roff[c]:roff[c + 1]], nat[c], g["volume"][c], g["energy"][c],
+                g["forces"][3 * aoff[c]:3 * aoff[c + 1]], g["stress"][c], g["eweight"][c], g["fweight"][c],
+                g["vweight"][c], types)
+    A, b, w, bad, batch = col.flush()
+    assert int(bad.item()) == 0 and batch.n_rows_out == g["ref_a"].shape[0]
+    assert np.array_equal(A.cpu().numpy(), g["ref_a"])
+    assert np.array_equal(b.cpu().numpy(), g["ref_b"]) and np.array_equal(w.cpu().numpy(), g["ref_w"])
