@@ -26,6 +26,9 @@ int fsb_launch_scatter(const fsb_context* h, const double* raw, const int64_t* r
                        int ncoeff, int flags, double* A, int64_t lda, double* b, double* w,
                        int32_t* nonfinite, const int32_t* row_cfg, int64_t n_rows_hint, cudaStream_t s);
 
+int fsb_launch_lasso(const fsb_context* h, const double* gaug, int k, double n_train, double alpha, int max_iter,
+                     double tol, double* x_out, int32_t* info, cudaStream_t s);
+
 static thread_local char g_cuda_err[512] = "";
 
 void fsb_note_cuda_error(cudaError_t e, const char* where) {
@@ -144,6 +147,13 @@ int fsb_factor_solve(fsb_handle_t h, const void* factor, int32_t k, const double
   if (!h || !factor || k < 1 || k > FSB_MAX_K || !rhs || rhs_stride < 1 || !x_out)
     return FSB_ERR_INVALID_ARGUMENT;
   return fsb_launch_factor_solve(h, factor, k, rhs, rhs_stride, alpha, x_in, x_out, (cudaStream_t)stream);
+}
+
+int fsb_lasso(fsb_handle_t h, const double* gaug, int32_t k, int64_t n_train, double alpha, int32_t max_iter,
+              double tol, double* x_out, int32_t* info, void* stream) {
+  if (!h || !gaug || k < 1 || k > FSB_MAX_K || n_train < 0 || !(alpha >= 0.0) || max_iter < 1 || !x_out || !info)
+    return FSB_ERR_INVALID_ARGUMENT;
+  return fsb_launch_lasso(h, gaug, k, (double)n_train, alpha, max_iter, tol, x_out, info, (cudaStream_t)stream);
 }
 
 size_t fsb_residual_workspace_bytes(fsb_handle_t h, int64_t n_rows, int32_t k) {

@@ -145,6 +145,16 @@ class Engine:
         self.launch_count += 1
         return x
 
+    def lasso(self, gaug, n_train, alpha, max_iter=2000, tol=1e-12):
+        """Coordinate descent on the reduced problem (lasso.py:25-29 objective)."""
+        k = gaug.shape[0] - 1
+        x = torch.empty(k, dtype=torch.float64, device=self.device)
+        info = torch.empty(2, dtype=torch.int32, device=self.device)
+        _cabi.check("fsb_lasso", self.lib.fsb_lasso(self._h, _ptr(gaug), k, int(n_train), float(alpha), int(max_iter),
+                                                     float(tol), _ptr(x), _ptr(info), self._stream()))
+        self.launch_count += 1
+        return x, info
+
     def residual(self, A, b, w, testing, x):
         """g = aw^T (bw - aw x) over this rank's rows."""
         n, k, lda = self._check_matrix(A, b, w, testing)

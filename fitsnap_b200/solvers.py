@@ -202,3 +202,46 @@ class RIDGE(LinearSolverBase):
             self.fit = res.coefficients()
             return
         super().perform_fit(a, b, w, fs_dict, trainall)
+
+
+class LASSO(LinearSolverBase):
+    """Drop-in for fitsnap3lib.solvers.lasso.LASSO: argmin 1/(2n)|aw x - bw|^2 + alpha |x|_1 with
+    alpha = [LASSO] alpha, at most [LASSO] max_iter sweeps (solver_sections/lasso.py:8-14).  The
+    reference runs sklearn's coordinate descent on the tall system (or, with `apply_transpose`, on
+    (aw^T aw, aw^T bw) -- lasso.py:22-24); here the Gram is formed once on the device and the
+    coordinate descent runs on the k x k problem.  Iterated to a tight tolerance (1e-12 relative
+    coordinate change), i.e. closer to the minimiser than sklearn's default tol = 1e-4 stop."""
+
+    tol = 1e-12
+
+    def __init__(self, name, pt, config):
+        super().__init__(name, pt, config)
+
+    def perform_fit(self, a=None, b=None, w=None, fs_dict=None, trainall=False):
+        if getattr(self.pt, "_rank", 0) != 0 and self.process_group is None:
+            return
+        sec = _section(self.config, "LASSO")
+        alpha = float(_get(sec, "alpha", 1.0e-8))
+        max_iter = int(_get(sec, "max_iter", 2000))
+        a, b, w, testing = self._resolve_inputs(a, b, w, fs_dict, trainall)
+        A, B, W, T = self._to_device(a, b, w, testing)
+        eng = self._engine()
+        gaug = eng.gram(A, B, W, T)
+        n_train = A.shape[0] if T is None else int(A.shape[0] - int(T.sum().item()))
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(gaug, group=self.process_group)
+            nt = torch.tensor([n_train], dtype=torch.float64, device=gaug.device)
+            dist.all_reduce(nt, group=self.process_group)
+            n_train = int(nt.item())
+        extras = _section(self.config, "EXTRAS")
+        if _get(extras, "apply_transpose", False):
+            # lasso.py:22-24: sklearn then sees X = aw^T aw (k rows), y = aw^T bw
+            k = gaug.shape[0] - 1
+            C = gaug[:k, :k].contiguous()
+            d = gaug[:k, k].contiguous()
+            gaug = eng.gram(C, d, torch.ones(k, dtype=torch.float64, device=C.device), None)
+            n_train = k
+        x, info = eng.lasso(gaug, n_train, alpha, max_iter, self.tol)
+        self.info = {"not_converged": int(info[0].item()), "sweeps": int(info[1].item())}
+        self.fit = x.detach().cpu().numpy().astype(np.float64, copy=True)

@@ -136,6 +136,16 @@ int fsb_factor_solve(fsb_handle_t h, const void* factor, int32_t k, const double
                      int64_t rhs_stride, double alpha, const double* x_in, double* x_out,
                      void* stream);
 
+/* ---- LASSO on the reduced problem ----------------------------------------------------
+ * Replaces sklearn Lasso(alpha, fit_intercept=False, max_iter).fit(aw, bw) as called at
+ * solvers/lasso.py:25-29: argmin 1/(2 n_train) |bw - aw x|^2 + alpha |x|_1, by cyclic coordinate
+ * descent on (G, c) taken from `gaug` (fsb_gram output).  Stops when the largest coordinate
+ * change of a sweep is <= tol * max|x| or after max_iter sweeps.
+ * info[0] = 0 converged / 1 hit max_iter, info[1] = sweeps done (device int32[2]).
+ */
+int fsb_lasso(fsb_handle_t h, const double* gaug, int32_t k, int64_t n_train, double alpha,
+              int32_t max_iter, double tol, double* x_out, int32_t* info, void* stream);
+
 /* ---- K7: residual / prediction pass --------------------------------------------------
  * fsb_residual: g = aw^T (bw - aw x) in one streaming pass over A (refinement residual;
  *   the reference computes `aw @ coef - bw` at solvers/ridge.py:60).

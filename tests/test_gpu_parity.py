@@ -370,3 +370,26 @@ def test_block_collector_stages_and_flushes(engine, tag):
     assert int(bad.item()) == 0 and batch.n_rows_out == g["ref_a"].shape[0]
     assert np.array_equal(A.cpu().numpy(), g["ref_a"])
     assert np.array_equal(b.cpu().numpy(), g["ref_b"]) and np.array_equal(w.cpu().numpy(), g["ref_w"])
+
+
+def test_lasso_matches_tightly_converged_sklearn(engine, ta):
+    """LASSO.perform_fit (lasso.py:15-30 objective).  sklearn's default stop (tol 1e-4) is loose, so the
+    comparison is against sklearn iterated to tol 1e-14, plus the reference result by objective value."""
+    from types import SimpleNamespace
+    from fitsnap_b200.solvers import LASSO
+    a, b, w, t = synth_system(**SOLVE_CASES["well"])
+    alpha = 1e-3
+    cfg = SimpleNamespace(sections={"LASSO": SimpleNamespace(alpha=alpha, max_iter=20000),
+                                    "EXTRAS": SimpleNamespace(apply_transpose=0)})
+    s = LASSO("LASSO", _pt(a, b, w, t), cfg)
+    s.perform_fit()
+    tight = lf.lasso_fit(a, b, w, alpha, 200000, t, tol=1e-14)
+    assert s.info["not_converged"] == 0
+    assert np.count_nonzero(s.fit) == np.count_nonzero(tight) and np.count_nonzero(s.fit) < len(tight)   # it is sparse
+    assert np.max(np.abs(s.fit - tight)) < 1e-8 * np.max(np.abs(tight))
+    # the reference's own (loosely converged) Ta result: ours must not have a worse objective
+    s2 = LASSO("LASSO", _pt(ta["a"], ta["b"], ta["w"]), SimpleNamespace(sections={
+        "LASSO": SimpleNamespace(alpha=1e-6, max_iter=20000), "EXTRAS": SimpleNamespace(apply_transpose=0)}))
+    s2.perform_fit()
+    aw, bw = lf.weighted_system(ta["a"], ta["b"], ta["w"])
+    assert lf.lasso_objective(aw, bw, s2.fit, 1e-6) <= lf.lasso_objective(aw, bw, ta["ref_lasso_1e6"], 1e-6) * (1 + 1e-9)
