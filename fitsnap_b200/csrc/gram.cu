@@ -28,6 +28,7 @@
 //     shape so no predicate sits between DMMAs.
 //   * split-K partials go to a workspace and are summed in a fixed order (deterministic).
 #include "fsb_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -373,12 +374,28 @@ GramPlan plan_gram(const fsb_context* h, int64_t n_rows, int k) {
 
 }  // namespace
 
+// narrow matrices (<= 13 blocks of 8 augmented columns) take the row-split kernel of gram_small.cu
+int fsb_gram_small_ctas(const fsb_context* h, int64_t n_rows);
+int fsb_gram_small_groups();
+int fsb_launch_gram_small(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* weff,
+                          int64_t n_rows, int k, double* partial, cudaStream_t s);
+static bool use_small(int k) { return (k + 1 + 7) / 8 <= 13; }
+
+static GramPlan effective_plan(const fsb_context* h, int64_t n_rows, int k) {
+  GramPlan pl = plan_gram(h, n_rows, k);
+  if (use_small(k)) {
+    pl.ntile = 1;
+    pl.nchunk = fsb_gram_small_ctas(h, n_rows) * fsb_gram_small_groups();
+  }
+  return pl;
+}
+
 static size_t partial_bytes(const GramPlan& pl) {
   return (size_t)pl.nchunk * pl.ntile * FSB_GT * FSB_GT * sizeof(double);
 }
 
 size_t fsb_gram_ws_bytes(const fsb_context* h, int64_t n_rows, int k) {
-  GramPlan pl = plan_gram(h, n_rows, k);
+  GramPlan pl = effective_plan(h, n_rows, k);
   // split-K partials + room for the masked weight vector (used only when a test mask is given)
   return partial_bytes(pl) + (size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double);
 }
@@ -386,7 +403,7 @@ size_t fsb_gram_ws_bytes(const fsb_context* h, int64_t n_rows, int k) {
 int fsb_launch_gram(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* w,
                     const uint8_t* testing, int64_t n_rows, int k, double* gaug, void* ws, size_t ws_bytes,
                     cudaStream_t s) {
-  GramPlan pl = plan_gram(h, n_rows, k);
+  GramPlan pl = effective_plan(h, n_rows, k);
   const size_t need = partial_bytes(pl) + (size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double);
   if (ws_bytes < need) return FSB_ERR_WORKSPACE_TOO_SMALL;
   const double* weff = w;
@@ -396,6 +413,16 @@ int fsb_launch_gram(const fsb_context* h, const double* A, int64_t lda, const do
     FSB_LAUNCH_CHECK("mask_weights_kernel");
     weff = wbuf;
   }
+  const int ka = k + 1;
+  dim3 rgrid((unsigned)fsb_ceil_div(ka, 32), (unsigned)ka);
+  if (use_small(k) && !getenv("FSB_GRAM_FORCE_TILED")) {
+    int st = fsb_launch_gram_small(h, A, lda, b, weff, n_rows, k, (double*)ws, s);
+    if (st != FSB_OK) return st;
+    gram_reduce_kernel<<<rgrid, 256, 0, s>>>((const double*)ws, pl.nchunk, 1, ka, gaug);
+    FSB_LAUNCH_CHECK("gram_reduce_kernel");
+    return FSB_OK;
+  }
+  pl = plan_gram(h, n_rows, k);
   GramArgs a;
   a.A = A; a.lda = lda; a.b = b; a.w = weff; a.n_rows = n_rows; a.k = k;
   a.ntile = pl.ntile; a.rows_per_chunk = pl.rows_per_chunk; a.partial = (double*)ws;
@@ -409,8 +436,6 @@ int fsb_launch_gram(const fsb_context* h, const double* A, int64_t lda, const do
     gram_dmma_kernel<false><<<(unsigned)(pl.nchunk * pl.ntile), FSB_GTHREADS, smem, s>>>(a);
   }
   FSB_LAUNCH_CHECK("gram_dmma_kernel");
-  const int ka = k + 1;
-  dim3 rgrid((unsigned)fsb_ceil_div(ka, 32), (unsigned)ka);
   gram_reduce_kernel<<<rgrid, 256, 0, s>>>((const double*)ws, pl.nchunk, pl.ntile, ka, gaug);
   FSB_LAUNCH_CHECK("gram_reduce_kernel");
   return FSB_OK;

@@ -339,34 +339,49 @@ __global__ void __launch_bounds__(512) small_factor_kernel(const double* __restr
   }
   __syncthreads();
 
-  const int tx = tid & 31, ty = tid >> 5, nty = nt >> 5;
-  for (int j = 0; j < k; ++j) {
-    const double pj = S[j * P + j];
-    const bool drop = !(pj > tol);
-    if (tid == 0) piv[j] = drop ? 0.0 : pj;
-    if (!drop) {
-      const double inv = 1.0 / pj;
-      // each lane keeps its (<= 4) column-j entries in registers; one warp per row, rows unrolled
-      // by two so the LDS -> DFMA -> STS chains of independent rows overlap
-      double lc[4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int c = j + 1 + tx + 32 * m;
-        lc[m] = (c < k) ? S[c * P + j] : 0.0;
-      }
-      for (int r = j + 1 + ty; r < k; r += 2 * nty) {
-        const int r2 = r + nty;
-        const double l1 = S[r * P + j] * inv;
-        const double l2 = (r2 < k) ? S[r2 * P + j] * inv : 0.0;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const int c = j + 1 + tx + 32 * m;
-          if (c <= r) S[r * P + c] -= l1 * lc[m];
-          if (r2 < k && c <= r2) S[r2 * P + c] -= l2 * lc[m];
+  // Blocked left-looking Cholesky, panels of PB columns.  (1) the panel is updated with all
+  // previous columns at once (every thread owns (row, panel column) elements and runs a dot product
+  // over the finished columns: no barrier inside), (2) the PB columns of the panel are factored one
+  // by one; only the panel is touched there, so those 2 barriers per column guard very little work.
+  // Columns are stored already scaled (true L); dropped columns are zeroed and flagged in piv[].
+  constexpr int PB = 16;
+  for (int p0 = 0; p0 < k; p0 += PB) {
+    const int pw = (k - p0) < PB ? (k - p0) : PB;
+    if (p0 > 0) {
+      const int nel = (k - p0) * PB;
+      for (int idx = tid; idx < nel; idx += nt) {
+        const int r = p0 + (idx >> 4), c = p0 + (idx & (PB - 1));
+        if (c < p0 + pw && c <= r) {
+          const double* sr = S + r * P;
+          const double* sc = S + c * P;
+          double acc = 0.0;
+          for (int m = 0; m < p0; ++m) acc += sr[m] * sc[m];
+          S[r * P + c] -= acc;
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
+    for (int j = p0; j < p0 + pw; ++j) {
+      const double pj = S[j * P + j];
+      const bool drop = !(pj > tol);
+      const double ljj = drop ? 1.0 : sqrt(pj);
+      const double inv = 1.0 / ljj;
+      __syncthreads();                       // everyone has read the pivot before it is overwritten
+      if (tid == 0) { piv[j] = drop ? 0.0 : pj; S[j * P + j] = ljj; }
+      for (int r = j + 1 + tid; r < k; r += nt) S[r * P + j] = drop ? 0.0 : S[r * P + j] * inv;
+      __syncthreads();
+      if (!drop) {
+        const int nc = p0 + pw - (j + 1);    // remaining panel columns
+        if (nc > 0) {
+          const int nel = (k - (j + 1)) * PB;
+          for (int idx = tid; idx < nel; idx += nt) {
+            const int r = j + 1 + (idx >> 4), c = j + 1 + (idx & (PB - 1));
+            if (c < p0 + pw && c <= r) S[r * P + c] -= S[r * P + j] * S[c * P + j];
+          }
+        }
+      }
+      __syncthreads();
+    }
   }
 
   // scale the columns, publish the factor in the common layout (pitch kp, identity padding)
@@ -376,9 +391,7 @@ __global__ void __launch_bounds__(512) small_factor_kernel(const double* __restr
     const int i = idx / kp, j = idx - i * kp;
     double v = 0.0;
     if (i < k && j <= i) {
-      const double pj = piv[j];
-      if (pj == 0.0) v = (i == j) ? 1.0 : 0.0;
-      else v = (i == j) ? sqrt(pj) : S[i * P + j] / sqrt(pj);
+      v = S[i * P + j];      // already the scaled factor; dropped columns hold (1 on the diagonal, 0 below)
     } else if (i == j) {
       v = 1.0;
     }
@@ -399,7 +412,10 @@ __global__ void __launch_bounds__(512) small_factor_kernel(const double* __restr
   }
 }
 
-// x_out = x_in + D L^-T L^-1 D (rhs - alpha x_in) for k <= 128: thread i owns component i, L in smem.
+// x_out = x_in + D L^-T L^-1 D (rhs - alpha x_in) for k <= 128.  All 128 threads stage L in shared
+// memory (coalesced rows); then ONE warp runs both substitutions with the vector in registers
+// (lane l owns rows l, l+32, l+64, l+96): per column one shuffle broadcast and <= 4 predicated
+// LDS+DFMA per lane, no block barrier in the dependent chain.
 __global__ void __launch_bounds__(SMALL_K) small_solve_kernel(FactorView f, int k, const double* __restrict__ rhs,
                                                               int64_t rhs_stride, double alpha,
                                                               const double* __restrict__ x_in,
@@ -407,35 +423,61 @@ __global__ void __launch_bounds__(SMALL_K) small_solve_kernel(FactorView f, int 
   extern __shared__ double sm[];
   const int P = k | 1;
   double* L = sm;               // k x P
-  double* bc = sm + (size_t)k * P;   // broadcast slot per column
   const int kp = f.kp;
-  const int i = threadIdx.x;
-  for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
-    const int r = idx / k, c = idx - r * k;
-    if (c <= r) L[r * P + c] = f.L[(size_t)r * kp + c];
-  }
-  double di = 0.0, xi = 0.0, y = 0.0, fl = 0.0, lii = 1.0;
-  if (i < k) {
-    di = f.d[i];
-    fl = f.flag[i];
-    xi = x_in ? x_in[i] : 0.0;
-    y = di * (rhs[(size_t)i * rhs_stride] - alpha * xi);
-  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int r = warp; r < k; r += nwarp)
+    for (int c = lane; c <= r; c += 32) L[r * P + c] = f.L[(size_t)r * kp + c];
   __syncthreads();
-  if (i < k) lii = 1.0 / L[i * P + i];   // reciprocal once: a double divide per column would dominate
-  // forward: L y = r (column oriented)
-  for (int j = 0; j < k; ++j) {
-    if (i == j) { y = (fl != 0.0) ? 0.0 : y * lii; bc[j] = y; }
-    __syncthreads();
-    if (i > j && i < k) y -= L[i * P + j] * bc[j];
+  if (warp != 0) return;
+
+  double y[4], dsc[4], xin[4], fl[4], invd[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int r = lane + 32 * s;
+    const bool live = r < k;
+    dsc[s] = live ? f.d[r] : 0.0;
+    fl[s] = live ? f.flag[r] : 0.0;
+    xin[s] = (live && x_in) ? x_in[r] : 0.0;
+    y[s] = live ? dsc[s] * (rhs[(size_t)r * rhs_stride] - alpha * xin[s]) : 0.0;
+    invd[s] = live ? 1.0 / L[r * P + r] : 1.0;
+  }
+  // forward: L y = r
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    for (int jj = 0; jj < 32; ++jj) {
+      const int j = 32 * s + jj;
+      if (j >= k) break;
+      if (lane == jj) y[s] = (fl[s] != 0.0) ? 0.0 : y[s] * invd[s];
+      const double yj = __shfl_sync(0xffffffffu, y[s], jj);
+#pragma unroll
+      for (int s2 = 0; s2 < 4; ++s2) {
+        if (s2 < s) continue;
+        const int r = lane + 32 * s2;
+        if (r > j && r < k) y[s2] -= L[r * P + j] * yj;
+      }
+    }
   }
   // backward: L^T z = y
-  for (int j = k - 1; j >= 0; --j) {
-    if (i == j) { y = y * lii; bc[j] = y; }
-    __syncthreads();
-    if (i < j) y -= L[j * P + i] * bc[j];
+#pragma unroll
+  for (int s = 3; s >= 0; --s) {
+    for (int jj = 31; jj >= 0; --jj) {
+      const int j = 32 * s + jj;
+      if (j >= k) continue;
+      if (lane == jj) y[s] = y[s] * invd[s];
+      const double zj = __shfl_sync(0xffffffffu, y[s], jj);
+#pragma unroll
+      for (int s2 = 0; s2 < 4; ++s2) {
+        if (s2 > s) continue;
+        const int r = lane + 32 * s2;
+        if (r < j) y[s2] -= L[j * P + r] * zj;
+      }
+    }
   }
-  if (i < k) x_out[i] = xi + di * y;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int r = lane + 32 * s;
+    if (r < k) x_out[r] = xin[s] + dsc[s] * y[s];
+  }
 }
 
 __global__ void init_info_kernel(int32_t* info, int k) {
@@ -489,7 +531,7 @@ int fsb_launch_factor_solve(const fsb_context* h, const void* factor, int k, con
   FactorView f = view_factor(const_cast<void*>(factor), k);
   if (k <= SMALL_K) {
     const int P = k | 1;
-    const size_t smem_s = ((size_t)k * P + (size_t)k) * sizeof(double);
+    const size_t smem_s = ((size_t)k * P) * sizeof(double);
     FSB_CUDA_TRY(cudaFuncSetAttribute(small_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
     small_solve_kernel<<<1, SMALL_K, smem_s, s>>>(f, k, rhs, rhs_stride, alpha, x_in, x_out);
     FSB_LAUNCH_CHECK("small_solve_kernel");

@@ -110,22 +110,22 @@ __global__ void __launch_bounds__(256, MINB) rowpass_kernel(const double* __rest
   }
 }
 
-// Deterministic column sums of the per-CTA partial vectors: 32 columns x 8 part-groups per block,
-// each group adds its parts in index order, the 8 group sums are combined in a fixed order.
-__global__ void __launch_bounds__(256) colsum_reduce_kernel(const double* __restrict__ partial, int nparts, int k,
-                                                            double* __restrict__ g) {
-  __shared__ double sh[8][33];
+// Deterministic column sums of the per-CTA partial vectors: 32 columns x 32 part-groups per block,
+// each group adds its parts in index order, the 32 group sums are combined in a fixed order.
+__global__ void __launch_bounds__(1024) colsum_reduce_kernel(const double* __restrict__ partial, int nparts, int k,
+                                                             double* __restrict__ g) {
+  __shared__ double sh[32][33];
   const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   double s = 0.0;
   if (c < k)
-    for (int p = gy; p < nparts; p += 8) s += partial[(size_t)p * k + c];
+    for (int p = gy; p < nparts; p += 32) s += partial[(size_t)p * k + c];
   sh[gy][cx] = s;
   __syncthreads();
   if (gy == 0 && c < k) {
     double t = 0.0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t += sh[q][cx];
+    for (int q = 0; q < 32; ++q) t += sh[q][cx];
     g[c] = t;
   }
 }
@@ -172,7 +172,7 @@ int launch_rowpass(const fsb_context* h, const double* A, int64_t lda, const dou
 #define FSB_ROWPASS1(NPL, RPI) FSB_ROWPASS_M(NPL, RPI, 1)
   if (npl <= 1) FSB_ROWPASS(1, 8);
   else if (npl <= 2) FSB_ROWPASS(2, 4);
-  else if (npl <= 4) FSB_ROWPASS(4, 4);
+  else if (npl <= 4) { if (getenv("FSB_ROWPASS_RPI8")) FSB_ROWPASS_M(4, 8, 1); else FSB_ROWPASS(4, 4); }
   else if (npl <= 8) FSB_ROWPASS(8, 2);
   else if (npl <= 16) FSB_ROWPASS1(16, 1);
   else if (npl <= 32) FSB_ROWPASS1(32, 1);
@@ -400,7 +400,7 @@ int fsb_launch_residual(const fsb_context* h, const double* A, int64_t lda, cons
   if (ws_bytes < (size_t)pl.ncta * k * sizeof(double)) return FSB_ERR_WORKSPACE_TOO_SMALL;
   int st = launch_rowpass<true>(h, A, lda, b, w, testing, n_rows, k, x, (double*)ws, s);
   if (st != FSB_OK) return st;
-  colsum_reduce_kernel<<<(unsigned)fsb_ceil_div(k, 32), 256, 0, s>>>((const double*)ws, pl.ncta, k, g);
+  colsum_reduce_kernel<<<(unsigned)fsb_ceil_div(k, 32), 1024, 0, s>>>((const double*)ws, pl.ncta, k, g);
   FSB_LAUNCH_CHECK("colsum_reduce_kernel");
   return FSB_OK;
 }
