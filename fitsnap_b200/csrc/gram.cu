@@ -66,6 +66,15 @@ __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc,
   const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gsrc), "r"(nbytes) : "memory");
 }
+// plain 16-byte copy (no src-size operand): the common case of a full stage
+__device__ __forceinline__ void cp_async16_full(double* smem_dst, const double* gsrc) {
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8_full(double* smem_dst, const double* gsrc) {
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -230,14 +239,14 @@ __global__ void __launch_bounds__(FSB_GTHREADS, 1) gram_dmma_kernel(GramArgs p) 
 #pragma unroll
         for (int i = 0; i < COPIES; ++i) {
           double* dI = st + (srow + ROW_GROUPS * i) * FSB_GLDS + scol;
-          if (modeI == 0) cp_async16(dI, runI, sI0.nbytes);
-          else if (modeI == 2) cp_async8(dI, runI, sI0.nbytes != 0);
+          if (modeI == 0) { if (sI0.nbytes) cp_async16_full(dI, runI); else cp_async16(dI, runI, 0); }
+          else if (modeI == 2) { if (sI0.nbytes) cp_async8_full(dI, runI); else cp_async8(dI, runI, false); }
           else copy_slot(dI, sI0, sI1, 1, r0 + srow + ROW_GROUPS * i, true);
           runI += stepI;
           if (!diag) {
             double* dJ = dI + RANGE_DOUBLES;
-            if (modeJ == 0) cp_async16(dJ, runJ, sJ0.nbytes);
-            else if (modeJ == 2) cp_async8(dJ, runJ, sJ0.nbytes != 0);
+            if (modeJ == 0) { if (sJ0.nbytes) cp_async16_full(dJ, runJ); else cp_async16(dJ, runJ, 0); }
+            else if (modeJ == 2) { if (sJ0.nbytes) cp_async8_full(dJ, runJ); else cp_async8(dJ, runJ, false); }
             else copy_slot(dJ, sJ0, sJ1, 1, r0 + srow + ROW_GROUPS * i, true);
             runJ += stepJ;
           }

@@ -224,15 +224,13 @@ def test_synthetic_svd_and_ridge(engine, name):
 
 
 def test_refinement_is_needed_and_works(engine):
-    """Plain normal equations miss 1e-10 on an ill-conditioned system (SURVEY hard part 2);
-    the streamed-residual refinement recovers it."""
-    g = load_golden("solve_ill.npz")
-    a, b, w, t = synth_system(**SOLVE_CASES["ill"])
-    x0, _ = fit_host(engine, a, b, w, t, refine=0)
-    x2, _ = fit_host(engine, a, b, w, t, refine=3)
-    e0 = lf.coeff_rel_err(x0, g["ref_svd"])[0]
-    e2 = lf.coeff_rel_err(x2, g["ref_svd"])[0]
-    assert e2 < 1e-10 < e0, (e0, e2)
+    """cond(G) = cond(w*A)^2: on the cond ~ 2e7 system the plain normal-equation solution misses the
+    1e-10 target by orders of magnitude (SURVEY hard part 2); refinement with the residual streamed
+    from A recovers it."""
+    g = load_golden("solve_hard.npz")
+    a, b, w, t = synth_system(**SOLVE_CASES["hard"])
+    errs = [lf.coeff_rel_err(fit_host(engine, a, b, w, t, refine=r)[0], g["ref_svd"])[1] for r in (0, 2, 4)]
+    assert errs[0] > 1e-9 and errs[1] < 1e-2 * errs[0] and errs[2] < 1e-11, errs
 
 
 def test_residual_and_predict(engine):
