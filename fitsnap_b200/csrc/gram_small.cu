@@ -34,6 +34,7 @@ struct SmallArgs {
   int k;
   int64_t rows_per_cta;
   double* partial;      // [cta * S_GROUPS + group][128][128]
+  int debug;            // tuning: bit0 = L2 prefetch in the flattened producer
 };
 
 constexpr int S_CONSUMERS = 256;   // warps 0-7
@@ -86,17 +87,24 @@ __device__ __forceinline__ void consume(const SmallArgs& p, const double* smem, 
     const int slot = s % nstage;
     bar_sync(1 + slot, S_THREADS);                       // FULL[slot]: the producers' stores are visible
     const double* st = smem + (size_t)slot * stage_doubles + frag_off;
+    // fragments of k-step q+1 are loaded before the DMMAs of k-step q are issued, so the LDS latency
+    // of one warp never coincides with an empty DMMA queue on its scheduler
+    constexpr int Q = S_RCH / 4 / S_GROUPS;
+    double f[2][R1 > 0 ? R1 : 1];
 #pragma unroll
-    for (int q = 0; q < S_RCH / 4 / S_GROUPS; ++q) {
-      const double* frow = st + (group + S_GROUPS * q) * 4 * pitch;   // this group's k-steps of the stage
-      double f[R1 > 0 ? R1 : 1];
+    for (int c = 0; c < R1; ++c) f[0][c] = st[group * 4 * pitch + c * 8];
 #pragma unroll
-      for (int c = 0; c < R1; ++c) f[c] = frow[c * 8];
+    for (int q = 0; q < Q; ++q) {
+      if (q + 1 < Q) {
+        const double* frow = st + (group + S_GROUPS * (q + 1)) * 4 * pitch;   // this group's next k-step
+#pragma unroll
+        for (int c = 0; c < R1; ++c) f[(q + 1) & 1][c] = frow[c * 8];
+      }
 #pragma unroll
       for (int i = R0; i < R1; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j)
-          dmma884(acc[i * (i + 1) / 2 + j - base][0], acc[i * (i + 1) / 2 + j - base][1], f[i], f[j]);
+          dmma884(acc[i * (i + 1) / 2 + j - base][0], acc[i * (i + 1) / 2 + j - base][1], f[q & 1][i], f[q & 1][j]);
     }
     if (s + nstage < nsteps) bar_arrive(1 + S_MAXSTAGE + slot, S_THREADS);   // EMPTY[slot]
   }
@@ -126,47 +134,112 @@ __global__ void __launch_bounds__(S_THREADS, 1) gram_rowsplit_kernel(SmallArgs p
   const int nsteps = row_end > row_begin ? (int)((row_end - row_begin + S_RCH - 1) / S_RCH) : 0;
 
   if (warp >= S_CONSUMERS / 32) {
+    if (KP >= 64) {
     // ------------------------------ producers: LDG -> weight -> STS ------------------------------
-    const int c = tid - S_CONSUMERS;            // column of the augmented matrix owned by this thread
-    const double* src; int64_t stride; bool use;
-    if (c < k) { src = p.A + c; stride = p.lda; use = true; }
-    else if (c == k) { src = p.b; stride = 1; use = true; }
-    else { src = p.w; stride = 0; use = false; }
+      const int c = tid - S_CONSUMERS;            // column of the augmented matrix owned by this thread
+      const double* src; int64_t stride; bool use;
+      if (c < k) { src = p.A + c; stride = p.lda; use = true; }
+      else if (c == k) { src = p.b; stride = 1; use = true; }
+      else { src = p.w; stride = 0; use = false; }
+      const int64_t last_row = p.n_rows > 0 ? p.n_rows - 1 : 0;
+      // Two register buffers: the loads of stage s+1 are in flight while stage s is weighted and
+      // stored, so a producer thread always has 32-64 independent 8-byte loads outstanding.
+      double va[S_RCH], vb[S_RCH];
+      double wa = 0.0, wb = 0.0;
+      auto load_stage = [&](int s, double (&v)[S_RCH], double& wl) {
+        const int64_t r0 = row_begin + (int64_t)s * S_RCH;
+        const int64_t rw = r0 + lane;                      // row weights: one coalesced load per warp
+        wl = (rw < row_end) ? __ldg(p.w + rw) : 0.0;
+        if (c < KP) {
+#pragma unroll
+          for (int i = 0; i < S_RCH; ++i) {
+            const int64_t r = r0 + i;
+            const int64_t rc = r < row_end ? r : last_row;   // clamped; rows past the end get weight 0
+            v[i] = __ldg(src + rc * stride);
+          }
+        }
+      };
+      auto store_stage = [&](int s, const double (&v)[S_RCH], double wl) {
+        const int slot = s % NSTAGE;
+        if (s >= NSTAGE) bar_sync(1 + S_MAXSTAGE + slot, S_THREADS);      // EMPTY[slot]: consumers are done with it
+        double* st = smem + (size_t)slot * (S_RCH * PITCH) + c;
+#pragma unroll
+        for (int i = 0; i < S_RCH; ++i) {
+          const double wi = __shfl_sync(0xffffffffu, wl, i);
+          if (c < KP) st[i * PITCH] = use ? v[i] * wi : 0.0;     // fl(w*a): the reference's aw (svd.py:44)
+        }
+        __threadfence_block();                                             // stores ordered before the arrival
+        bar_arrive(1 + slot, S_THREADS);                                   // FULL[slot]
+      };
+      if (nsteps > 0) load_stage(0, va, wa);
+      for (int s = 0; s < nsteps; s += 2) {
+        if (s + 1 < nsteps) load_stage(s + 1, vb, wb);
+        store_stage(s, va, wa);
+        if (s + 1 < nsteps) {
+          if (s + 2 < nsteps) load_stage(s + 2, va, wa);
+          store_stage(s + 1, vb, wb);
+        }
+      }
+
+      return;
+    }
+    // ------------------------------ producers: LDG -> weight -> STS ------------------------------
+    // The stage (S_RCH rows x KP columns) is flattened over the 128 producer threads so that every
+    // thread owns EPT elements whatever KP is; consecutive threads read consecutive addresses.
+    constexpr int NEL = S_RCH * KP;
+    constexpr int EPT = (NEL + S_PRODUCERS - 1) / S_PRODUCERS;
+    const int tp = tid - S_CONSUMERS;
     const int64_t last_row = p.n_rows > 0 ? p.n_rows - 1 : 0;
-    // Two register buffers: the loads of stage s+1 are in flight while stage s is weighted and
-    // stored, so a producer thread always has 32-64 independent 8-byte loads outstanding.
-    double va[S_RCH], vb[S_RCH];
+    double va[EPT], vb[EPT];
     double wa = 0.0, wb = 0.0;
-    auto load_stage = [&](int s, double (&v)[S_RCH], double& wl) {
+    auto load_stage = [&](int s, double (&v)[EPT], double& wl) {
       const int64_t r0 = row_begin + (int64_t)s * S_RCH;
       const int64_t rw = r0 + lane;                      // row weights: one coalesced load per warp
       wl = (rw < row_end) ? __ldg(p.w + rw) : 0.0;
-      if (c < KP) {
 #pragma unroll
-        for (int i = 0; i < S_RCH; ++i) {
-          const int64_t r = r0 + i;
-          const int64_t rc = r < row_end ? r : last_row;   // clamped; rows past the end get weight 0
-          v[i] = __ldg(src + rc * stride);
-        }
+      for (int i = 0; i < EPT; ++i) {
+        const int e = tp + S_PRODUCERS * i;
+        const int row = e / KP, col = e - row * KP;        // KP is a compile-time constant
+        const int64_t r = r0 + row;
+        const int64_t rc = r < row_end ? r : last_row;     // clamped; rows past the end get weight 0
+        const double* src = (col < k) ? p.A + rc * p.lda + col : ((col == k) ? p.b + rc : p.w);
+        v[i] = (e < NEL) ? __ldg(src) : 0.0;
       }
     };
-    auto store_stage = [&](int s, const double (&v)[S_RCH], double wl) {
+    auto store_stage = [&](int s, const double (&v)[EPT], double wl) {
       const int slot = s % NSTAGE;
       if (s >= NSTAGE) bar_sync(1 + S_MAXSTAGE + slot, S_THREADS);      // EMPTY[slot]: consumers are done with it
-      double* st = smem + (size_t)slot * (S_RCH * PITCH) + c;
+      double* st = smem + (size_t)slot * (S_RCH * PITCH);
 #pragma unroll
-      for (int i = 0; i < S_RCH; ++i) {
-        const double wi = __shfl_sync(0xffffffffu, wl, i);
-        if (c < KP) st[i * PITCH] = use ? v[i] * wi : 0.0;     // fl(w*a): the reference's aw (svd.py:44)
+      for (int i = 0; i < EPT; ++i) {
+        const int e = tp + S_PRODUCERS * i;
+        const int row = e / KP, col = e - row * KP;
+        const double wi = __shfl_sync(0xffffffffu, wl, row & 31);       // row < 32 whenever e < NEL
+        if (e < NEL) st[row * PITCH + col] = (col <= k) ? v[i] * wi : 0.0;   // fl(w*a): the reference's aw (svd.py:44)
       }
       __threadfence_block();                                             // stores ordered before the arrival
       bar_arrive(1 + slot, S_THREADS);                                   // FULL[slot]
     };
+    // DRAM latency is taken out of the demand loads by prefetching the rows of stage s+3 into L2
+    // (one prefetch per 128-byte line, spread over the producer threads; no registers tied up).
+    auto prefetch_stage = [&](int s) {
+      if (s >= nsteps || !(p.debug & 1)) return;
+      const int64_t r0 = row_begin + (int64_t)s * S_RCH;
+      const int64_t nr = (row_end - r0) < S_RCH ? (row_end - r0) : S_RCH;
+      const char* base = reinterpret_cast<const char*>(p.A + r0 * p.lda);
+      const int64_t nbytes = ((nr - 1) * p.lda + k) * (int64_t)sizeof(double);
+      for (int64_t off = (int64_t)tp * 128; off < nbytes; off += (int64_t)S_PRODUCERS * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+    };
+    constexpr int PF = 3;
+    for (int s = 1; s <= PF; ++s) prefetch_stage(s);
     if (nsteps > 0) load_stage(0, va, wa);
     for (int s = 0; s < nsteps; s += 2) {
+      prefetch_stage(s + 1 + PF);
       if (s + 1 < nsteps) load_stage(s + 1, vb, wb);
       store_stage(s, va, wa);
       if (s + 1 < nsteps) {
+        prefetch_stage(s + 2 + PF);
         if (s + 2 < nsteps) load_stage(s + 2, va, wa);
         store_stage(s + 1, vb, wb);
       }
@@ -213,6 +286,7 @@ int fsb_launch_gram_small(const fsb_context* h, const double* A, int64_t lda, co
   const int nb = (k + 1 + 7) / 8;
   SmallArgs a;
   a.A = A; a.lda = lda; a.b = b; a.w = weff; a.n_rows = n_rows; a.k = k; a.partial = partial;
+  { const char* e = getenv("FSB_GRAM_DEBUG"); a.debug = e ? atoi(e) : 0; }
   const int want = fsb_gram_small_ctas(h, n_rows);
   a.rows_per_cta = fsb_round_up(fsb_ceil_div(n_rows > 0 ? n_rows : 1, want), S_RCH);
   // every (cta < want, group) slot of the workspace must be written: launch `want` CTAs; surplus
