@@ -14,13 +14,15 @@
 //     are computed; the final reduction mirrors them.
 //   * grid = (#lower-tri super-tiles) x (#row chunks); blockIdx is tile-fastest so the CTAs
 //     that share a row chunk run together and re-reads of A hit the 126 MB L2.
-//   * each CTA streams its row chunk through a 3-stage cp.async (LDGSTS) ring of 32-row stages:
-//     global -> shared memory with no register staging, zero-fill for rows/columns past the
-//     edge, one __syncthreads per stage.  lda is arbitrary (K = 31, 69, 110 ... are real
-//     FitSNAP widths), so the copies are 8-byte; TMA needs 16-byte pitches and is not used here.
-//   * row weights (0 for test rows) ride along in the stage and are applied when a DMMA
-//     fragment is read from shared memory: fl(w*a), the same rounding as the reference's aw.
-//     The multiplies run on the plain fp64 pipe, which is separate from the DMMA sub-pipe.
+//   * warp-specialised CTA of 640 threads: 4 PRODUCER warps stage 16-row slices of the two column
+//     ranges of the super-tile (plain coalesced LDG -> weight/mask/b-column/zero padding -> STS)
+//     into a 6-deep shared-memory ring, 16 CONSUMER warps do nothing but LDS + DMMA.  FULL[s] /
+//     EMPTY[s] named barriers (bar.sync / bar.arrive) hand the stages over.  cp.async (LDGSTS)
+//     was measured at ~46 cycles per warp instruction per SM on this part and, issued by the
+//     compute warps, serialised with the DMMAs; TMA needs 16-byte row pitches, which real FitSNAP
+//     widths (31, 69, 110 ...) with lda = k do not give.  No alignment requirement here.
+//   * weights (0 for test rows) are applied by the producers, once per element: fl(w*a), the
+//     same rounding as the reference's aw; the consumers issue no fp64 op besides DMMA.
 //   * smem row pitch 132 doubles (== 4 mod 16) makes every fragment load conflict-free.
 //   * the 16 warp tiles (32x32 each) of a partial / diagonal super-tile carry unequal DMMA
 //     counts: they are dealt to warps by a longest-processing-time greedy so the four DMMA
@@ -44,40 +46,25 @@ struct GramArgs {
   double* partial;
 };
 
-constexpr int RCH = FSB_GRCH;                    // rows per stage
-constexpr int NSTAGE = 3;
+constexpr int RCH = 16;                          // rows per stage
+constexpr int NSTAGE = 6;                        // ring depth: 6 x 33.8 KB
 constexpr int RANGE_DOUBLES = RCH * FSB_GLDS;    // one column range of one stage
-constexpr int STAGE_DOUBLES = 2 * RANGE_DOUBLES + RCH;   // I range, J range, weights
+constexpr int STAGE_DOUBLES = 2 * RANGE_DOUBLES; // I range, J range
+constexpr int N_CONSUMERS = FSB_GTHREADS;        // 512: warps 0-15
+constexpr int N_PRODUCERS = 128;                 // warps 16-19
+constexpr int N_THREADS = N_CONSUMERS + N_PRODUCERS;
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
-
-// 8-byte asynchronous global->shared copy; src_bytes = 0 zero-fills without touching memory.
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
-  const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int nbytes = valid ? 8 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(saddr), "l"(gsrc), "r"(nbytes) : "memory");
+__device__ __forceinline__ void bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
-// 16-byte variant (both addresses 16-byte aligned)
-__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int nbytes) {
-  const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gsrc), "r"(nbytes) : "memory");
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
-// plain 16-byte copy (no src-size operand): the common case of a full stage
-__device__ __forceinline__ void cp_async16_full(double* smem_dst, const double* gsrc) {
-  const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async8_full(double* smem_dst, const double* gsrc) {
-  const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void tile_coords(int tile, int& ti, int& tj) {
   int t = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
@@ -91,19 +78,18 @@ __device__ __forceinline__ void tile_coords(int tile, int& ti, int& tj) {
 // diagonal of a diagonal super-tile: only blocks j <= i, and the B fragments are the A fragments).
 template <int MI, int NJ, bool OND>
 __device__ __forceinline__ void compute_stage(double (&acc)[4][4][2], const double* __restrict__ fI,
-                                              const double* __restrict__ fJ, const double* __restrict__ fW) {
-#pragma unroll 2
+                                              const double* __restrict__ fJ) {
+#pragma unroll
   for (int ks = 0; ks < RCH / 4; ++ks) {
-    const double wv = fW[ks * 4];
     double af[MI], bf[NJ];
 #pragma unroll
-    for (int i = 0; i < MI; ++i) af[i] = fI[ks * 4 * FSB_GLDS + i * 8] * wv;
+    for (int i = 0; i < MI; ++i) af[i] = fI[ks * 4 * FSB_GLDS + i * 8];
     if (OND) {
 #pragma unroll
       for (int j = 0; j < NJ; ++j) bf[j] = af[j];
     } else {
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) bf[j] = fJ[ks * 4 * FSB_GLDS + j * 8] * wv;
+      for (int j = 0; j < NJ; ++j) bf[j] = fJ[ks * 4 * FSB_GLDS + j * 8];
     }
 #pragma unroll
     for (int i = 0; i < MI; ++i)
@@ -113,9 +99,8 @@ __device__ __forceinline__ void compute_stage(double (&acc)[4][4][2], const doub
   }
 }
 
-template <bool VEC16>
-__global__ void __launch_bounds__(FSB_GTHREADS, 1) gram_dmma_kernel(GramArgs p) {
-  extern __shared__ double smem[];  // [NSTAGE][ I: RCH x GLDS | J: RCH x GLDS | w: RCH ]
+__global__ void __launch_bounds__(N_THREADS, 1) gram_dmma_kernel(GramArgs p) {
+  extern __shared__ double smem[];  // [NSTAGE][ I: RCH x GLDS | J: RCH x GLDS ]
 
   const int tile = blockIdx.x % p.ntile;
   const int64_t chunk = blockIdx.x / p.ntile;
@@ -133,7 +118,7 @@ __global__ void __launch_bounds__(FSB_GTHREADS, 1) gram_dmma_kernel(GramArgs p) 
   int nbI = (ka - colI0 + 7) >> 3; nbI = nbI > 16 ? 16 : nbI;
   int nbJ = (ka - colJ0 + 7) >> 3; nbJ = nbJ > 16 ? 16 : nbJ;
 
-  // Deal the 16 warp tiles to warps (LPT greedy over the four schedulers, warp % 4).
+  // Deal the 16 warp tiles to the consumer warps (LPT greedy over the four schedulers, warp % 4).
   __shared__ unsigned char s_map[16];
   if (tid == 0) {
     int cost[16], order[16], load[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
@@ -160,6 +145,56 @@ __global__ void __launch_bounds__(FSB_GTHREADS, 1) gram_dmma_kernel(GramArgs p) 
     }
   }
   __syncthreads();
+
+  const int64_t row_begin = chunk * p.rows_per_chunk;
+  int64_t row_end = row_begin + p.rows_per_chunk;
+  if (row_end > p.n_rows) row_end = p.n_rows;
+  const int nsteps = row_end > row_begin ? (int)((row_end - row_begin + RCH - 1) / RCH) : 0;
+
+  if (warp >= N_CONSUMERS / 32) {
+    // ------------------------------ producers: LDG -> weight -> STS ------------------------------
+    // thread c owns column c of the I range and column c of the J range; the source of a column is
+    // a per-thread constant: a column of A, the b vector (column k), or nothing (zero padding).
+    const int c = tid - N_CONSUMERS;
+    const int gcI = colI0 + c, gcJ = colJ0 + c;
+    const double* srcI; int64_t strI; bool useI;
+    const double* srcJ; int64_t strJ; bool useJ;
+    if (gcI < k) { srcI = p.A + gcI; strI = p.lda; useI = true; }
+    else if (gcI == k) { srcI = p.b; strI = 1; useI = true; }
+    else { srcI = p.w; strI = 0; useI = false; }
+    if (diag) { srcJ = p.w; strJ = 0; useJ = false; }
+    else if (gcJ < k) { srcJ = p.A + gcJ; strJ = p.lda; useJ = true; }
+    else if (gcJ == k) { srcJ = p.b; strJ = 1; useJ = true; }
+    else { srcJ = p.w; strJ = 0; useJ = false; }
+    const int64_t last_row = p.n_rows > 0 ? p.n_rows - 1 : 0;
+    for (int s = 0; s < nsteps; ++s) {
+      const int slot = s % NSTAGE;
+      const int64_t r0 = row_begin + (int64_t)s * RCH;
+      const int64_t rw = r0 + (lane & (RCH - 1));       // row weights: lanes 0..15 hold the stage's w
+      const double wl = (rw < row_end) ? __ldg(p.w + rw) : 0.0;
+      double vI[RCH], vJ[RCH];
+#pragma unroll
+      for (int i = 0; i < RCH; ++i) {
+        const int64_t r = r0 + i;
+        const int64_t rc = r < row_end ? r : last_row;   // clamped; rows past the end get weight 0
+        vI[i] = __ldg(srcI + rc * strI);
+        if (!diag) vJ[i] = __ldg(srcJ + rc * strJ);
+      }
+      if (s >= NSTAGE) bar_sync(1 + NSTAGE + slot, N_THREADS);      // EMPTY[slot]
+      double* stI = smem + (size_t)slot * STAGE_DOUBLES + c;
+#pragma unroll
+      for (int i = 0; i < RCH; ++i) {
+        const double wi = __shfl_sync(0xffffffffu, wl, i);
+        stI[i * FSB_GLDS] = useI ? vI[i] * wi : 0.0;                  // fl(w*a): the reference's aw (svd.py:44)
+        if (!diag) stI[RANGE_DOUBLES + i * FSB_GLDS] = useJ ? vJ[i] * wi : 0.0;
+      }
+      __threadfence_block();
+      bar_arrive(1 + slot, N_THREADS);                               // FULL[slot]
+    }
+    return;
+  }
+
+  // -------------------------------- consumers: LDS -> DMMA ---------------------------------------
   const int wt = s_map[warp];
   const int wr = wt >> 2, wc = wt & 3;
   int mi = nbI - 4 * wr; mi = mi > 4 ? 4 : mi;
@@ -169,145 +204,36 @@ __global__ void __launch_bounds__(FSB_GTHREADS, 1) gram_dmma_kernel(GramArgs p) 
   // shape code for the specialised inner loops (warp-uniform)
   const int shape = !active ? -1 : (on_diag ? 16 + (mi - 1) : (mi - 1) * 4 + (nj - 1));
 
-  const int64_t row_begin = chunk * p.rows_per_chunk;
-  int64_t row_end = row_begin + p.rows_per_chunk;
-  if (row_end > p.n_rows) row_end = p.n_rows;
-  const int nsteps = row_end > row_begin ? (int)((row_end - row_begin + RCH - 1) / RCH) : 0;
-
-  // ---- copy plan ------------------------------------------------------------------------------
-  // A "slot" is what one thread copies per stage row: 8 bytes of one column (scalar plan) or 16
-  // bytes of a column pair (VEC16: lda even and A 16-byte aligned).  The source of a slot is a
-  // per-thread constant: a column of A, the b vector (column k), or nothing (zero-fill).
-  constexpr int SLOTS_PER_ROW = VEC16 ? FSB_GT / 2 : FSB_GT;
-  constexpr int ROW_GROUPS = FSB_GTHREADS / SLOTS_PER_ROW;      // 8 (VEC16) or 4
-  constexpr int COPIES = RCH / ROW_GROUPS;                      // 4 (VEC16) or 8 per range per stage
-  const int slot = tid % SLOTS_PER_ROW;
-  const int srow = tid / SLOTS_PER_ROW;
-  const int scol = VEC16 ? 2 * slot : slot;
-  const int64_t last_row = p.n_rows > 0 ? p.n_rows - 1 : 0;
-
-  struct Src { const double* ptr; int64_t stride; int nbytes; };
-  auto scalar_src = [&](int gc) {
-    Src r;
-    if (gc < k) { r.ptr = p.A + gc; r.stride = p.lda; r.nbytes = 8; }
-    else if (gc == k) { r.ptr = p.b; r.stride = 1; r.nbytes = 8; }
-    else { r.ptr = p.w; r.stride = 0; r.nbytes = 0; }
-    return r;
-  };
-  // per range: mode 0 = one 16-byte copy from A, 1 = two scalar slots (pair straddles column k),
-  // 2 = scalar plan (one 8-byte slot)
-  Src sI0, sI1, sJ0, sJ1;
-  int modeI, modeJ;
-  {
-    const int gc = colI0 + scol;
-    if (VEC16) {
-      if (gc + 1 < k) { modeI = 0; sI0.ptr = p.A + gc; sI0.stride = p.lda; sI0.nbytes = 16; sI1 = sI0; }
-      else if (gc > k) { modeI = 0; sI0.ptr = p.w; sI0.stride = 0; sI0.nbytes = 0; sI1 = sI0; }
-      else { modeI = 1; sI0 = scalar_src(gc); sI1 = scalar_src(gc + 1); }
-    } else { modeI = 2; sI0 = scalar_src(gc); sI1 = sI0; }
-    const int gj = colJ0 + scol;
-    if (VEC16) {
-      if (gj + 1 < k) { modeJ = 0; sJ0.ptr = p.A + gj; sJ0.stride = p.lda; sJ0.nbytes = 16; sJ1 = sJ0; }
-      else if (gj > k) { modeJ = 0; sJ0.ptr = p.w; sJ0.stride = 0; sJ0.nbytes = 0; sJ1 = sJ0; }
-      else { modeJ = 1; sJ0 = scalar_src(gj); sJ1 = scalar_src(gj + 1); }
-    } else { modeJ = 2; sJ0 = scalar_src(gj); sJ1 = sJ0; }
-  }
-
-  auto copy_slot = [&](double* dst, const Src& s0, const Src& s1, int mode, int64_t rc, bool in) {
-    if (mode == 0) cp_async16(dst, s0.ptr + rc * s0.stride, in ? s0.nbytes : 0);
-    else {
-      cp_async8(dst, s0.ptr + rc * s0.stride, in && s0.nbytes);
-      if (mode == 1) cp_async8(dst + 1, s1.ptr + rc * s1.stride, in && s1.nbytes);
-    }
-  };
-
-  // Running source pointers: the rows a thread copies form one arithmetic progression across
-  // stages (srow, srow+RG, ..., then the same rows of the next stage), so every copy costs one
-  // 64-bit add instead of a 64-bit multiply-add plus clamps.  Stages are issued in order.
-  const double* runI = sI0.ptr + (row_begin + srow) * sI0.stride;
-  const double* runJ = sJ0.ptr + (row_begin + srow) * sJ0.stride;
-  const int64_t stepI = (int64_t)ROW_GROUPS * sI0.stride;
-  const int64_t stepJ = (int64_t)ROW_GROUPS * sJ0.stride;
-  const double* runW = p.w + row_begin + (tid < RCH ? tid : 0);
-
-  auto issue_stage = [&](int step) {
-    if (step < nsteps) {
-      double* st = smem + (size_t)(step % NSTAGE) * STAGE_DOUBLES;
-      const int64_t r0 = row_begin + (int64_t)step * RCH;
-      const bool full = (r0 + RCH <= row_end);       // every stage but the last of a chunk
-      if (full) {
-#pragma unroll
-        for (int i = 0; i < COPIES; ++i) {
-          double* dI = st + (srow + ROW_GROUPS * i) * FSB_GLDS + scol;
-          if (modeI == 0) { if (sI0.nbytes) cp_async16_full(dI, runI); else cp_async16(dI, runI, 0); }
-          else if (modeI == 2) { if (sI0.nbytes) cp_async8_full(dI, runI); else cp_async8(dI, runI, false); }
-          else copy_slot(dI, sI0, sI1, 1, r0 + srow + ROW_GROUPS * i, true);
-          runI += stepI;
-          if (!diag) {
-            double* dJ = dI + RANGE_DOUBLES;
-            if (modeJ == 0) { if (sJ0.nbytes) cp_async16_full(dJ, runJ); else cp_async16(dJ, runJ, 0); }
-            else if (modeJ == 2) { if (sJ0.nbytes) cp_async8_full(dJ, runJ); else cp_async8(dJ, runJ, false); }
-            else copy_slot(dJ, sJ0, sJ1, 1, r0 + srow + ROW_GROUPS * i, true);
-            runJ += stepJ;
-          }
-        }
-        if (tid < RCH) cp_async8(st + 2 * RANGE_DOUBLES + tid, runW, true);
-        runW += RCH;
-      } else {   // ragged last stage of the chunk: per-row predicate, clamped addresses
-#pragma unroll
-        for (int i = 0; i < COPIES; ++i) {
-          const int lr = srow + ROW_GROUPS * i;
-          const int64_t r = r0 + lr;
-          const bool in = r < row_end;
-          const int64_t rc = in ? r : last_row;
-          copy_slot(st + lr * FSB_GLDS + scol, sI0, sI1, modeI, rc, in);
-          if (!diag) copy_slot(st + RANGE_DOUBLES + lr * FSB_GLDS + scol, sJ0, sJ1, modeJ, rc, in);
-        }
-        if (tid < RCH) {
-          const int64_t r = r0 + tid;
-          const bool in = r < row_end;
-          cp_async8(st + 2 * RANGE_DOUBLES + tid, p.w + (in ? r : last_row), in);
-        }
-      }
-    }
-    cp_async_commit();   // always commit (possibly empty) so the group accounting stays uniform
-  };
-
   double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-#pragma unroll
-  for (int s = 0; s < NSTAGE - 1; ++s) issue_stage(s);
-
   const int frag_off = (lane & 3) * FSB_GLDS + (lane >> 2);
   for (int s = 0; s < nsteps; ++s) {
-    cp_async_wait<NSTAGE - 2>();   // this thread's copies of stage s have landed
-    __syncthreads();               // everyone's have, and everyone is done reading stage s-1
-    issue_stage(s + NSTAGE - 1);   // refill the buffer stage s-1 used
+    const int slot = s % NSTAGE;
+    bar_sync(1 + slot, N_THREADS);                                   // FULL[slot]
     if (active) {
-      const double* st = smem + (size_t)(s % NSTAGE) * STAGE_DOUBLES;
+      const double* st = smem + (size_t)slot * STAGE_DOUBLES;
       const double* fI = st + frag_off + wr * 32;
       const double* fJ = (diag ? st : st + RANGE_DOUBLES) + frag_off + wc * 32;
-      const double* fW = st + 2 * RANGE_DOUBLES + (lane & 3);
       switch (shape) {
-#define FSB_CASE(MI, NJ) case (MI - 1) * 4 + (NJ - 1): compute_stage<MI, NJ, false>(acc, fI, fJ, fW); break;
+#define FSB_CASE(MI, NJ) case (MI - 1) * 4 + (NJ - 1): compute_stage<MI, NJ, false>(acc, fI, fJ); break;
         FSB_CASE(4, 4) FSB_CASE(4, 3) FSB_CASE(4, 2) FSB_CASE(4, 1)
         FSB_CASE(3, 4) FSB_CASE(3, 3) FSB_CASE(3, 2) FSB_CASE(3, 1)
         FSB_CASE(2, 4) FSB_CASE(2, 3) FSB_CASE(2, 2) FSB_CASE(2, 1)
         FSB_CASE(1, 4) FSB_CASE(1, 3) FSB_CASE(1, 2) FSB_CASE(1, 1)
 #undef FSB_CASE
-        case 16: compute_stage<1, 1, true>(acc, fI, fJ, fW); break;
-        case 17: compute_stage<2, 2, true>(acc, fI, fJ, fW); break;
-        case 18: compute_stage<3, 3, true>(acc, fI, fJ, fW); break;
-        case 19: compute_stage<4, 4, true>(acc, fI, fJ, fW); break;
+        case 16: compute_stage<1, 1, true>(acc, fI, fJ); break;
+        case 17: compute_stage<2, 2, true>(acc, fI, fJ); break;
+        case 18: compute_stage<3, 3, true>(acc, fI, fJ); break;
+        case 19: compute_stage<4, 4, true>(acc, fI, fJ); break;
         default: break;
       }
     }
+    if (s + NSTAGE < nsteps) bar_arrive(1 + NSTAGE + slot, N_THREADS);   // EMPTY[slot]
   }
-  cp_async_wait<0>();
 
   // split-K partial: [chunk][tile][128][128]; only entries that the reduction reads need be valid
   if (active) {
@@ -373,10 +299,10 @@ GramPlan plan_gram(const fsb_context* h, int64_t n_rows, int k) {
   pl.ntile = nt * (nt + 1) / 2;
   // one resident CTA per SM (512 threads x <=128 regs); several waves when tiles are heterogeneous
   int64_t want = pl.ntile == 1 ? h->sm_count : fsb_ceil_div(8 * (int64_t)h->sm_count, pl.ntile);
-  int64_t max_chunks = fsb_ceil_div(n_rows > 0 ? n_rows : 1, 4 * FSB_GRCH);
+  int64_t max_chunks = fsb_ceil_div(n_rows > 0 ? n_rows : 1, 4 * RCH);
   if (want > max_chunks) want = max_chunks;
   if (want < 1) want = 1;
-  pl.rows_per_chunk = fsb_round_up(fsb_ceil_div(n_rows > 0 ? n_rows : 1, want), FSB_GRCH);
+  pl.rows_per_chunk = fsb_round_up(fsb_ceil_div(n_rows > 0 ? n_rows : 1, want), RCH);
   pl.nchunk = (int)fsb_ceil_div(n_rows > 0 ? n_rows : 1, pl.rows_per_chunk);
   return pl;
 }
@@ -436,14 +362,8 @@ int fsb_launch_gram(const fsb_context* h, const double* A, int64_t lda, const do
   a.A = A; a.lda = lda; a.b = b; a.w = weff; a.n_rows = n_rows; a.k = k;
   a.ntile = pl.ntile; a.rows_per_chunk = pl.rows_per_chunk; a.partial = (double*)ws;
   const size_t smem = (size_t)NSTAGE * STAGE_DOUBLES * sizeof(double);
-  const bool vec16 = (lda % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-  if (vec16) {
-    FSB_CUDA_TRY(cudaFuncSetAttribute(gram_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gram_dmma_kernel<true><<<(unsigned)(pl.nchunk * pl.ntile), FSB_GTHREADS, smem, s>>>(a);
-  } else {
-    FSB_CUDA_TRY(cudaFuncSetAttribute(gram_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gram_dmma_kernel<false><<<(unsigned)(pl.nchunk * pl.ntile), FSB_GTHREADS, smem, s>>>(a);
-  }
+  FSB_CUDA_TRY(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gram_dmma_kernel<<<(unsigned)(pl.nchunk * pl.ntile), N_THREADS, smem, s>>>(a);
   FSB_LAUNCH_CHECK("gram_dmma_kernel");
   gram_reduce_kernel<<<rgrid, 256, 0, s>>>((const double*)ws, pl.nchunk, pl.ntile, ka, gaug);
   FSB_LAUNCH_CHECK("gram_reduce_kernel");
