@@ -316,6 +316,18 @@ int fsb_launch_gram_small(const fsb_context* h, const double* A, int64_t lda, co
                           int64_t n_rows, int k, double* partial, cudaStream_t s);
 static bool use_small(int k) { return (k + 1 + 7) / 8 <= 13; }
 
+// wide matrices: pre-weight pass + TMA-fed kernel (gram_tma.cu); the LDG-staged kernel above is the
+// fallback when the driver entry point for tensor maps is unavailable or FSB_GRAM_NO_TMA is set
+int64_t fsb_gram_tma_ldw(int k);
+bool fsb_gram_tma_available();
+int fsb_launch_gram_tma(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* weff,
+                        int64_t n_rows, int k, int ntile, int nchunk, int64_t rows_per_chunk, double* partial,
+                        double* waug, cudaStream_t s);
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+static size_t waug_bytes(int64_t n_rows, int k) {
+  return use_small(k) ? 0 : align256((size_t)(n_rows > 0 ? n_rows : 1) * (size_t)fsb_gram_tma_ldw(k) * sizeof(double));
+}
+
 static GramPlan effective_plan(const fsb_context* h, int64_t n_rows, int k) {
   GramPlan pl = plan_gram(h, n_rows, k);
   if (use_small(k)) {
@@ -331,19 +343,22 @@ static size_t partial_bytes(const GramPlan& pl) {
 
 size_t fsb_gram_ws_bytes(const fsb_context* h, int64_t n_rows, int k) {
   GramPlan pl = effective_plan(h, n_rows, k);
-  // split-K partials + room for the masked weight vector (used only when a test mask is given)
-  return partial_bytes(pl) + (size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double);
+  // split-K partials + masked weight vector (test mask given) + pre-weighted copy (wide matrices)
+  return align256(partial_bytes(pl)) + align256((size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double)) +
+         waug_bytes(n_rows, k);
 }
 
 int fsb_launch_gram(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* w,
                     const uint8_t* testing, int64_t n_rows, int k, double* gaug, void* ws, size_t ws_bytes,
                     cudaStream_t s) {
   GramPlan pl = effective_plan(h, n_rows, k);
-  const size_t need = partial_bytes(pl) + (size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double);
+  const size_t off_w = align256(partial_bytes(pl));
+  const size_t off_waug = off_w + align256((size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double));
+  const size_t need = off_waug + waug_bytes(n_rows, k);
   if (ws_bytes < need) return FSB_ERR_WORKSPACE_TOO_SMALL;
   const double* weff = w;
   if (testing && n_rows > 0) {
-    double* wbuf = (double*)((char*)ws + partial_bytes(pl));
+    double* wbuf = (double*)((char*)ws + off_w);
     mask_weights_kernel<<<(unsigned)fsb_ceil_div(n_rows, 256), 256, 0, s>>>(w, testing, n_rows, wbuf);
     FSB_LAUNCH_CHECK("mask_weights_kernel");
     weff = wbuf;
@@ -358,6 +373,14 @@ int fsb_launch_gram(const fsb_context* h, const double* A, int64_t lda, const do
     return FSB_OK;
   }
   pl = plan_gram(h, n_rows, k);
+  if (fsb_gram_tma_available() && (reinterpret_cast<uintptr_t>(ws) & 127) == 0) {
+    int st = fsb_launch_gram_tma(h, A, lda, b, weff, n_rows, k, pl.ntile, pl.nchunk, pl.rows_per_chunk,
+                                 (double*)ws, (double*)((char*)ws + off_waug), s);
+    if (st != FSB_OK) return st;
+    gram_reduce_kernel<<<rgrid, 256, 0, s>>>((const double*)ws, pl.nchunk, pl.ntile, ka, gaug);
+    FSB_LAUNCH_CHECK("gram_reduce_kernel");
+    return FSB_OK;
+  }
   GramArgs a;
   a.A = A; a.lda = lda; a.b = b; a.w = weff; a.n_rows = n_rows; a.k = k;
   a.ntile = pl.ntile; a.rows_per_chunk = pl.rows_per_chunk; a.partial = (double*)ws;
