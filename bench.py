@@ -416,7 +416,7 @@ def main():
                              (n_rows * k * 8 / 1e6, n_rows * (kraw + 1) * 8 / 1e6)},
             "gram_tflops_algorithmic": achieved,
             "gram_ms": gram_ms,
-            "roofline": {"kernel": "gram_dmma_kernel (+reduce)", "bound": "tensor", "achieved": achieved,
+            "roofline": {"kernel": ("gram_rowsplit_kernel" if k + 1 <= 104 else ("gram_dmma_kernel" if k + 1 <= 128 else "preweight_kernel + gram_tma_kernel")) + " (+gram_reduce_kernel)", "bound": "tensor", "achieved": achieved,
                          "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak, "traffic": None,
                          "peak_kind": "dense bf16 cuBLAS, %s (MEASURED_PEAKS.json)" % peak_kind,
                          "fp64_note": "tcgen05 has no f64 kind; this kernel runs on DMMA.8x8x4 whose measured peak "

@@ -325,7 +325,7 @@ int fsb_launch_gram_tma(const fsb_context* h, const double* A, int64_t lda, cons
                         double* waug, cudaStream_t s);
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t waug_bytes(int64_t n_rows, int k) {
-  return use_small(k) ? 0 : align256((size_t)(n_rows > 0 ? n_rows : 1) * (size_t)fsb_gram_tma_ldw(k) * sizeof(double));
+  return (k + 1 <= FSB_GT) ? 0 : align256((size_t)(n_rows > 0 ? n_rows : 1) * (size_t)fsb_gram_tma_ldw(k) * sizeof(double));
 }
 
 static GramPlan effective_plan(const fsb_context* h, int64_t n_rows, int k) {
@@ -373,7 +373,9 @@ int fsb_launch_gram(const fsb_context* h, const double* A, int64_t lda, const do
     return FSB_OK;
   }
   pl = plan_gram(h, n_rows, k);
-  if (fsb_gram_tma_available() && (reinterpret_cast<uintptr_t>(ws) & 127) == 0) {
+  // one super-tile (k + 1 <= 128): every column is read once, the pre-weight pass would double the
+  // traffic for nothing -> LDG-staged kernel; three tiles and more: pre-weight + TMA
+  if (pl.ntile >= 3 && fsb_gram_tma_available() && (reinterpret_cast<uintptr_t>(ws) & 127) == 0) {
     int st = fsb_launch_gram_tma(h, A, lda, b, weff, n_rows, k, pl.ntile, pl.nchunk, pl.rows_per_chunk,
                                  (double*)ws, (double*)((char*)ws + off_waug), s);
     if (st != FSB_OK) return st;

@@ -11,6 +11,8 @@
 //   d[kp]      power-of-two column scales (0 => coefficient pinned to 0)
 //   flag[kp]   1.0 => column dropped during factorisation (pivot below tolerance)
 //   L[kp*kp]   row-major, pitch kp; lower triangle holds the Cholesky factor of S = D (G+alpha I) D
+//   Linv[kp*32] (k <= 128) inverses of the 32x32 diagonal blocks of L: the small solve is then four
+//              block steps of tiny mat-vecs instead of k dependent scalar steps
 //
 // The factorisation is a right-looking blocked Cholesky with 64-wide panels, three small
 // kernels per panel (diag potrf / panel trsm / trailing syrk).  k <= 1024 means <= 48
@@ -28,6 +30,7 @@ struct FactorView {
   double* d;
   double* flag;
   double* L;
+  double* Linv;   // k <= 128 only: inverses of the 32x32 diagonal blocks of L, [kp/32][32][32]
   int kp;
 };
 
@@ -38,6 +41,7 @@ __host__ __device__ inline FactorView view_factor(void* buf, int k) {
   v.d = (double*)buf;
   v.flag = v.d + v.kp;
   v.L = v.flag + v.kp;
+  v.Linv = v.L + (size_t)v.kp * v.kp;
   return v;
 }
 
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(NB) trsm_panel_kernel(FactorView f, int p) {
   const double* dblk = f.L + (size_t)(p * NB) * kp + p * NB;
   for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
     const int r = idx / NB, c = idx % NB;
-    lpp[r][c] = dblk[(size_t)r * kp + c];
+    lpp[r][c] = __ldg(dblk + (size_t)r * kp + c);
   }
   if (threadIdx.x < NB) fl[threadIdx.x] = f.flag[p * NB + threadIdx.x];
   __syncthreads();
@@ -186,8 +190,8 @@ __global__ void __launch_bounds__(256) syrk_update_kernel(FactorView f, int p) {
   for (int mh = 0; mh < NB; mh += MH) {
     for (int idx = threadIdx.x; idx < NB * MH; idx += blockDim.x) {
       const int r = idx / MH, c = idx % MH;
-      la[r][c] = pa[(size_t)r * kp + mh + c];
-      lb[r][c] = pb[(size_t)r * kp + mh + c];
+      la[r][c] = __ldg(pa + (size_t)r * kp + mh + c);
+      lb[r][c] = __ldg(pb + (size_t)r * kp + mh + c);
     }
     __syncthreads();
     for (int m = 0; m < MH; ++m) {
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(256) trsv_kernel(FactorView f, int k, const do
     const double* dblk = f.L + (size_t)(p * NB) * kp + p * NB;
     for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
       const int r = idx / NB, c = idx % NB;
-      blk[r * NBP + c] = dblk[(size_t)r * kp + c];
+      blk[r * NBP + c] = __ldg(dblk + (size_t)r * kp + c);
     }
     if (tid < NB) s_flag[tid] = f.flag[p * NB + tid];
     __syncthreads();
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(256) trsv_kernel(FactorView f, int k, const do
     const double y0 = y[p * NB + lane], y1 = y[p * NB + 32 + lane];
     for (int i = (p + 1) * NB + warp; i < kp; i += nwarp) {
       const double* lrow = f.L + (size_t)i * kp + p * NB;
-      double part = lrow[lane] * y0 + lrow[32 + lane] * y1;
+      double part = __ldg(lrow + lane) * y0 + __ldg(lrow + 32 + lane) * y1;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
       if (lane == 0) y[i] -= part;
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(256) trsv_kernel(FactorView f, int k, const do
     const double* dblk = f.L + (size_t)(p * NB) * kp + p * NB;
     for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
       const int r = idx / NB, c = idx % NB;
-      blk[r * NBP + c] = dblk[(size_t)r * kp + c];
+      blk[r * NBP + c] = __ldg(dblk + (size_t)r * kp + c);
     }
     __syncthreads();
     if (warp == 0) {
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(256) trsv_kernel(FactorView f, int k, const do
       double part = 0.0;
       const double* lcol = f.L + (size_t)(p * NB) * kp + j;
 #pragma unroll 8
-      for (int r = 0; r < NB; ++r) part += lcol[(size_t)r * kp] * y[p * NB + r];
+      for (int r = 0; r < NB; ++r) part += __ldg(lcol + (size_t)r * kp) * y[p * NB + r];
       y[j] -= part;
     }
     __syncthreads();
@@ -328,13 +332,15 @@ __global__ void __launch_bounds__(512) small_factor_kernel(const double* __restr
     dsc[i] = (g > 0.0 && g < DBL_MAX) ? pow2_scale(g) : 0.0;
   }
   __syncthreads();
-  for (int idx = tid; idx < k * k; idx += nt) {
-    const int i = idx / k, j = idx - i * k;
-    if (j > i) continue;
+#pragma unroll 4
+  for (int idx = tid; idx < k * ka; idx += nt) {      // flat over the first k rows of gaug: coalesced, unrolled
+    const int i = idx / ka, j = idx - i * ka;
+    const double g = gaug[idx];
+    if (j > i || j >= k) continue;
     const double di = dsc[i], dj = dsc[j];
     double v;
     if (di == 0.0 || dj == 0.0) v = (i == j) ? 1.0 : 0.0;
-    else v = di * (gaug[(size_t)i * ka + j] + (i == j ? alpha : 0.0)) * dj;
+    else v = di * (g + (i == j ? alpha : 0.0)) * dj;
     S[i * P + j] = v;
   }
   __syncthreads();
@@ -397,6 +403,28 @@ __global__ void __launch_bounds__(512) small_factor_kernel(const double* __restr
     }
     f.L[(size_t)i * kp + j] = v;
   }
+  // inverses of the 32x32 diagonal blocks (warp b inverts block b; lane c owns column c of the inverse
+  // and runs a forward substitution on e_c with the block's rows broadcast from shared memory)
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nb32 = kp / 32;
+    if (warp < nb32) {
+      const int o = warp * 32;
+      double x[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int gi = o + i;
+        double acc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int m = 0; m < 32; ++m)
+          if (m < i) acc -= ((gi < k) ? S[gi * P + o + m] : 0.0) * x[m];
+        const double lii = (gi < k) ? S[gi * P + gi] : 1.0;
+        x[i] = (i >= lane) ? acc / lii : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f.Linv[(size_t)warp * 1024 + i * 32 + lane] = x[i];
+    }
+  }
   for (int i = tid; i < kp; i += nt) {
     const bool real = i < k;
     const bool dropped = real && piv[i] == 0.0 && dsc[i] != 0.0;
@@ -412,72 +440,81 @@ __global__ void __launch_bounds__(512) small_factor_kernel(const double* __restr
   }
 }
 
-// x_out = x_in + D L^-T L^-1 D (rhs - alpha x_in) for k <= 128.  All 128 threads stage L in shared
-// memory (coalesced rows); then ONE warp runs both substitutions with the vector in registers
-// (lane l owns rows l, l+32, l+64, l+96): per column one shuffle broadcast and <= 4 predicated
-// LDS+DFMA per lane, no block barrier in the dependent chain.
+// x_out = x_in + D L^-T L^-1 D (rhs - alpha x_in) for k <= 128, blocked by 32: with the inverses of
+// the diagonal blocks precomputed by small_factor_kernel a substitution is 4 block steps, each two
+// tiny mat-vecs done by the whole CTA (4 threads per row, shuffle-combined), instead of k dependent
+// scalar steps.  128 threads: thread t -> row (t >> 2) of the current block, quarter (t & 3).
 __global__ void __launch_bounds__(SMALL_K) small_solve_kernel(FactorView f, int k, const double* __restrict__ rhs,
                                                               int64_t rhs_stride, double alpha,
                                                               const double* __restrict__ x_in,
                                                               double* __restrict__ x_out) {
   extern __shared__ double sm[];
-  const int P = k | 1;
-  double* L = sm;               // k x P
-  const int kp = f.kp;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int r = warp; r < k; r += nwarp)
-    for (int c = lane; c <= r; c += 32) L[r * P + c] = f.L[(size_t)r * kp + c];
+  const int kp = f.kp;                   // 64 or 128
+  const int P = kp | 1;
+  double* L = sm;                        // kp x P (lower triangle used)
+  double* Li = L + (size_t)kp * P;       // [kp/32][32][33]
+  double* y = Li + (size_t)(kp / 32) * 32 * 33;   // kp
+  double* tb = y + kp;                   // 32 (block right-hand side)
+  const int tid = threadIdx.x, nt = blockDim.x;
+  {
+    const int nel = kp * kp;
+#pragma unroll 8
+    for (int idx = tid; idx < nel; idx += nt) {
+      const int r = idx / kp, c = idx - r * kp;
+      const double v = __ldg(f.L + idx);
+      if (c <= r) L[r * P + c] = v;
+    }
+    const int nli = (kp / 32) * 1024;
+#pragma unroll 4
+    for (int idx = tid; idx < nli; idx += nt) {
+      const int b = idx >> 10, r = (idx >> 5) & 31, c = idx & 31;
+      Li[(b * 32 + r) * 33 + c] = __ldg(f.Linv + idx);
+    }
+  }
+  for (int i = tid; i < kp; i += nt) {
+    double v = 0.0;
+    if (i < k) v = f.d[i] * (rhs[(size_t)i * rhs_stride] - alpha * (x_in ? x_in[i] : 0.0));
+    y[i] = v;
+  }
   __syncthreads();
-  if (warp != 0) return;
-
-  double y[4], dsc[4], xin[4], fl[4], invd[4];
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int r = lane + 32 * s;
-    const bool live = r < k;
-    dsc[s] = live ? f.d[r] : 0.0;
-    fl[s] = live ? f.flag[r] : 0.0;
-    xin[s] = (live && x_in) ? x_in[r] : 0.0;
-    y[s] = live ? dsc[s] * (rhs[(size_t)r * rhs_stride] - alpha * xin[s]) : 0.0;
-    invd[s] = live ? 1.0 / L[r * P + r] : 1.0;
+  const int nb32 = kp / 32;
+  const int row = tid >> 2, q = tid & 3;     // 32 rows x 4 quarters
+  // ---- forward: L y = r
+  for (int b = 0; b < nb32; ++b) {
+    const int gi = b * 32 + row;
+    double part = 0.0;
+    const int ncol = b * 32;                 // columns already solved
+    for (int c = q; c < ncol; c += 4) part += L[gi * P + c] * y[c];
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (q == 0) tb[row] = y[gi] - part;
+    __syncthreads();
+    double acc = 0.0;
+    for (int m = q; m <= row; m += 4) acc += Li[(b * 32 + row) * 33 + m] * tb[m];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    __syncthreads();                         // everyone is done reading tb / y of this block
+    if (q == 0) y[gi] = (gi < k && f.flag[gi] != 0.0) ? 0.0 : acc;
+    __syncthreads();
   }
-  // forward: L y = r
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    for (int jj = 0; jj < 32; ++jj) {
-      const int j = 32 * s + jj;
-      if (j >= k) break;
-      if (lane == jj) y[s] = (fl[s] != 0.0) ? 0.0 : y[s] * invd[s];
-      const double yj = __shfl_sync(0xffffffffu, y[s], jj);
-#pragma unroll
-      for (int s2 = 0; s2 < 4; ++s2) {
-        if (s2 < s) continue;
-        const int r = lane + 32 * s2;
-        if (r > j && r < k) y[s2] -= L[r * P + j] * yj;
-      }
-    }
+  // ---- backward: L^T z = y
+  for (int b = nb32 - 1; b >= 0; --b) {
+    const int gi = b * 32 + row;
+    double part = 0.0;
+    for (int c = (b + 1) * 32 + q; c < kp; c += 4) part += L[c * P + gi] * y[c];   // (L^T)[gi][c] = L[c][gi]
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (q == 0) tb[row] = y[gi] - part;
+    __syncthreads();
+    double acc = 0.0;
+    for (int m = row + q; m < 32; m += 4) acc += Li[(b * 32 + m) * 33 + row] * tb[m];   // (Linv^T)[row][m]
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    __syncthreads();
+    if (q == 0) y[gi] = acc;
+    __syncthreads();
   }
-  // backward: L^T z = y
-#pragma unroll
-  for (int s = 3; s >= 0; --s) {
-    for (int jj = 31; jj >= 0; --jj) {
-      const int j = 32 * s + jj;
-      if (j >= k) continue;
-      if (lane == jj) y[s] = y[s] * invd[s];
-      const double zj = __shfl_sync(0xffffffffu, y[s], jj);
-#pragma unroll
-      for (int s2 = 0; s2 < 4; ++s2) {
-        if (s2 > s) continue;
-        const int r = lane + 32 * s2;
-        if (r < j) y[s2] -= L[j * P + r] * zj;
-      }
-    }
-  }
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int r = lane + 32 * s;
-    if (r < k) x_out[r] = xin[s] + dsc[s] * y[s];
-  }
+  for (int i = tid; i < k; i += nt) x_out[i] = (x_in ? x_in[i] : 0.0) + f.d[i] * y[i];
 }
 
 __global__ void init_info_kernel(int32_t* info, int k) {
@@ -489,7 +526,7 @@ __global__ void init_info_kernel(int32_t* info, int k) {
 size_t fsb_factor_bytes_impl(int k) {
   int kp = ((k + NB - 1) / NB) * NB;
   if (kp == 0) kp = NB;
-  return ((size_t)2 * kp + (size_t)kp * kp) * sizeof(double);
+  return ((size_t)2 * kp + (size_t)kp * kp + (size_t)kp * 32) * sizeof(double);
 }
 
 int fsb_launch_factor(const fsb_context* h, const double* gaug, int k, double alpha, void* factor,
@@ -530,8 +567,8 @@ int fsb_launch_factor_solve(const fsb_context* h, const void* factor, int k, con
                             cudaStream_t s) {
   FactorView f = view_factor(const_cast<void*>(factor), k);
   if (k <= SMALL_K) {
-    const int P = k | 1;
-    const size_t smem_s = ((size_t)k * P) * sizeof(double);
+    const int kp_s = f.kp, P = kp_s | 1;
+    const size_t smem_s = ((size_t)kp_s * P + (size_t)(kp_s / 32) * 32 * 33 + kp_s + 32) * sizeof(double);
     FSB_CUDA_TRY(cudaFuncSetAttribute(small_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
     small_solve_kernel<<<1, SMALL_K, smem_s, s>>>(f, k, rhs, rhs_stride, alpha, x_in, x_out);
     FSB_LAUNCH_CHECK("small_solve_kernel");

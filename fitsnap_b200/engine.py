@@ -122,7 +122,7 @@ class Engine:
         _cabi.check("fsb_gram", self.lib.fsb_gram(self._h, _ptr(A), lda, _ptr(b), _ptr(w), _ptr(testing), n, k,
                                                    _ptr(gaug), _ptr(ws), ws.numel(), self._stream()))
         # narrow: row-split kernel + reduce; wide: pre-weight + TMA kernel + reduce
-        self.launch_count += (2 if (k + 8) // 8 <= 13 else 3) + (1 if (testing is not None and n > 0) else 0)
+        self.launch_count += (2 if k + 1 <= 128 else 3) + (1 if (testing is not None and n > 0) else 0)
         return gaug
 
     def factor(self, gaug, alpha=0.0):
