@@ -36,6 +36,7 @@ SIGNATURES = {
     "fsb_lasso": (c_int, [c_void_p, _P, c_int32, c_int64, c_double, c_int32, c_double, _P, _P, c_void_p]),
     "fsb_residual_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int32]),
     "fsb_residual": (c_int, [c_void_p, _P, c_int64, _P, _P, _P, c_int64, c_int32, _P, _P, _P, c_size_t, c_void_p]),
+    "fsb_group_stats": (c_int, [c_void_p, _P, c_int64, _P, _P, _P, c_int64, c_int32, _P, c_int32, _P, c_void_p]),
     "fsb_predict": (c_int, [c_void_p, _P, c_int64, c_int64, c_int32, _P, _P, c_void_p]),
 }
 

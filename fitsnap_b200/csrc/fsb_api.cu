@@ -29,6 +29,10 @@ int fsb_launch_scatter(const fsb_context* h, const double* raw, const int64_t* r
 int fsb_launch_lasso(const fsb_context* h, const double* gaug, int k, double n_train, double alpha, int max_iter,
                      double tol, double* x_out, int32_t* info, cudaStream_t s);
 
+int fsb_launch_group_stats(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* w,
+                           const int32_t* gid, int64_t n_rows, int k, const double* x, int n_groups, double* stats,
+                           cudaStream_t s);
+
 static thread_local char g_cuda_err[512] = "";
 
 void fsb_note_cuda_error(cudaError_t e, const char* where) {
@@ -169,6 +173,15 @@ int fsb_residual(fsb_handle_t h, const double* A, int64_t lda, const double* b, 
   if (n_rows > 0 && (!A || !b || !w)) return FSB_ERR_INVALID_ARGUMENT;
   return fsb_launch_residual(h, A, lda, b, w, testing, n_rows, k, x, g, workspace, workspace_bytes,
                              (cudaStream_t)stream);
+}
+
+int fsb_group_stats(fsb_handle_t h, const double* A, int64_t lda, const double* b, const double* w,
+                    const int32_t* group_id, int64_t n_rows, int32_t k, const double* x, int32_t n_groups,
+                    double* stats, void* stream) {
+  if (!h || k < 1 || k > FSB_MAX_K || n_rows < 0 || lda < k || !x || !stats || n_groups < 1)
+    return FSB_ERR_INVALID_ARGUMENT;
+  if (n_rows > 0 && (!A || !b || !w || !group_id)) return FSB_ERR_INVALID_ARGUMENT;
+  return fsb_launch_group_stats(h, A, lda, b, w, group_id, n_rows, k, x, n_groups, stats, (cudaStream_t)stream);
 }
 
 int fsb_predict(fsb_handle_t h, const double* A, int64_t lda, int64_t n_rows, int32_t k, const double* x,

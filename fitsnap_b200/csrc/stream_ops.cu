@@ -145,6 +145,84 @@ __global__ void __launch_bounds__(1024) colsum_reduce_kernel(const double* __res
   }
 }
 
+// ------------------------------------------------------------------------------ error analysis
+// Per-(group, train/test, row type) error sums of the linear error analysis
+// (fitsnap3lib/solvers/solver.py:108-133, 368-429) in ONE pass over A: pred = a . x, res = b - pred.
+// stats[g][0..9] = n, sum|res|, sum res^2, sum t, sum t^2, n(w != 0), sum|w res|, sum (w res)^2, sum w t, sum (w t)^2.
+// Each warp walks a CONTIGUOUS row range and keeps the sums of the current group in registers (rows
+// of one configuration / row type are adjacent), flushing to a shared-memory table only when the
+// group id changes; the table goes to global memory with one atomicAdd per non-zero entry per CTA.
+// (Atomic accumulation order is not fixed: metrics agree to rounding, not bit for bit.)
+constexpr int GS_NSTAT = 10;
+
+template <int NPL>
+__global__ void __launch_bounds__(256) group_stats_kernel(const double* __restrict__ A, int64_t lda,
+                                                          const double* __restrict__ b,
+                                                          const double* __restrict__ w,
+                                                          const int32_t* __restrict__ gid, int64_t n_rows, int k,
+                                                          const double* __restrict__ x, int n_groups,
+                                                          double* __restrict__ stats, int64_t rows_per_warp) {
+  extern __shared__ double tab[];   // n_groups x GS_NSTAT
+  for (int i = threadIdx.x; i < n_groups * GS_NSTAT; i += blockDim.x) tab[i] = 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double xr[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int c = lane + 32 * i;
+    xr[i] = (c < k) ? x[c] : 0.0;
+  }
+  const int64_t r_begin = warp_global * rows_per_warp;
+  int64_t r_end = r_begin + rows_per_warp;
+  if (r_end > n_rows) r_end = n_rows;
+  double acc[GS_NSTAT];
+#pragma unroll
+  for (int q = 0; q < GS_NSTAT; ++q) acc[q] = 0.0;
+  int cur = -1;
+  auto flush = [&]() {
+    if (cur >= 0 && lane == 0) {
+#pragma unroll
+      for (int q = 0; q < GS_NSTAT; ++q)
+        if (acc[q] != 0.0) atomicAdd(&tab[cur * GS_NSTAT + q], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < GS_NSTAT; ++q) acc[q] = 0.0;
+  };
+  constexpr int RPI = (NPL <= 4) ? 4 : (NPL <= 8 ? 2 : 1);
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += RPI) {
+    double a[RPI][NPL];
+#pragma unroll
+    for (int q = 0; q < RPI; ++q) {
+      const int64_t rc = (r0 + q < r_end) ? r0 + q : r_end - 1;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int c = lane + 32 * i;
+        a[q][i] = (c < k) ? __ldg(A + rc * lda + c) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RPI; ++q) {
+      if (r0 + q >= r_end) break;
+      double dot = 0.0;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) dot += a[q][i] * xr[i];
+      dot = warp_sum(dot);
+      const int64_t r = r0 + q;
+      const int g = gid[r];
+      if (g != cur) { flush(); cur = g; }
+      const double t = b[r], wv = w[r];
+      const double res = t - dot, wres = wv * res, wt = wv * t;
+      acc[0] += 1.0; acc[1] += fabs(res); acc[2] += res * res; acc[3] += t; acc[4] += t * t;
+      acc[5] += (wv != 0.0) ? 1.0 : 0.0; acc[6] += fabs(wres); acc[7] += wres * wres; acc[8] += wt; acc[9] += wt * wt;
+    }
+  }
+  flush();
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_groups * GS_NSTAT; i += blockDim.x)
+    if (tab[i] != 0.0) atomicAdd(&stats[i], tab[i]);
+}
+
 struct RowPlan {
   int ncta;
   int64_t rows_per_cta;
@@ -424,6 +502,40 @@ int fsb_launch_residual(const fsb_context* h, const double* A, int64_t lda, cons
   if (st != FSB_OK) return st;
   colsum_reduce_kernel<<<(unsigned)fsb_ceil_div(k, 32), 1024, 0, s>>>((const double*)ws, pl.ncta, k, g);
   FSB_LAUNCH_CHECK("colsum_reduce_kernel");
+  return FSB_OK;
+}
+
+int fsb_launch_group_stats(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* w,
+                           const int32_t* gid, int64_t n_rows, int k, const double* x, int n_groups, double* stats,
+                           cudaStream_t s) {
+  if (n_rows == 0) return FSB_OK;
+  const size_t smem = (size_t)n_groups * GS_NSTAT * sizeof(double);
+  if (smem > h->smem_optin) return FSB_ERR_UNSUPPORTED;
+  int64_t nwarps = (int64_t)h->sm_count * 8 * 4;
+  const int64_t maxw = fsb_ceil_div(n_rows, 32);
+  if (nwarps > maxw) nwarps = maxw;
+  if (nwarps < 8) nwarps = 8;
+  nwarps = fsb_round_up(nwarps, 8);
+  const int64_t rows_per_warp = fsb_ceil_div(n_rows, nwarps);
+  const int ncta = (int)(nwarps / 8);
+  const int npl = (k + 31) / 32;
+#define FSB_GS(NPL)                                                                                          \
+  do {                                                                                                       \
+    FSB_CUDA_TRY(cudaFuncSetAttribute(group_stats_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                      (int)smem));                                                           \
+    group_stats_kernel<NPL><<<ncta, 256, smem, s>>>(A, lda, b, w, gid, n_rows, k, x, n_groups, stats,        \
+                                                    rows_per_warp);                                          \
+  } while (0)
+  if (npl <= 1) FSB_GS(1);
+  else if (npl <= 2) FSB_GS(2);
+  else if (npl <= 4) FSB_GS(4);
+  else if (npl <= 8) FSB_GS(8);
+  else if (npl <= 16) FSB_GS(16);
+  else if (npl <= 32) FSB_GS(32);
+  else if (npl <= 64) FSB_GS(64);
+  else return FSB_ERR_UNSUPPORTED;
+#undef FSB_GS
+  FSB_LAUNCH_CHECK("group_stats_kernel");
   return FSB_OK;
 }
 

@@ -177,6 +177,17 @@ class Engine:
         self.launch_count += 1 if n > 0 else 0
         return y
 
+    def group_stats(self, A, b, w, group_id, x, n_groups):
+        """Per-group error sums (n_groups x 10) for the linear error analysis, one pass over A."""
+        n, k, lda = self._check_matrix(A, b, w, None)
+        assert group_id.dtype == torch.int32 and group_id.numel() == n and group_id.is_contiguous()
+        stats = torch.zeros((int(n_groups), 10), dtype=torch.float64, device=self.device)
+        _cabi.check("fsb_group_stats", self.lib.fsb_group_stats(self._h, _ptr(A), lda, _ptr(b), _ptr(w), _ptr(group_id),
+                                                                 n, k, _ptr(x), int(n_groups), _ptr(stats),
+                                                                 self._stream()))
+        self.launch_count += 1 if n > 0 else 0
+        return stats
+
     def scatter(self, batch, A=None, b=None, w=None, lda=None):
         """Assemble rows of (A, b, w) from a `ConfigBatch` already on the device."""
         k = batch.k

@@ -148,6 +148,25 @@ class LinearSolverBase:
         self._check_info(res)
         self.fit = res.coefficients()
 
+    def error_analysis_device(self, a=None, b=None, w=None, fs_dict=None):
+        """Linear error analysis (solver.py:368-429) from device-side sums: fills `self.errors` with
+        the same table the reference builds through a full pandas frame.  `self.fit` must be set.
+        Inputs default to pt.shared_arrays / pt.fitsnap_dict like the reference's error_analysis."""
+        from . import errors as _errors
+        if a is None and b is None and w is None and fs_dict is None:
+            dev = getattr(self.pt, "fitsnap_b200_device", None)
+            nb = self.pt.shared_arrays["b"].array.shape[0]
+            if dev is not None and dev["first_row"] == 0 and dev["n_rows"] == nb:
+                a, b, w = dev["A"], dev["b"], dev["w"]
+            else:
+                a = self.pt.shared_arrays["a"].array
+                b = self.pt.shared_arrays["b"].array
+                w = self.pt.shared_arrays["w"].array
+            fs_dict = self.pt.fitsnap_dict
+        fit = np.asarray(self.fit, dtype=np.float64).reshape(-1)
+        self.errors = _errors.linear_error_analysis(self._engine(), a, b, w, fs_dict, fit)
+        return self.errors
+
     def _check_info(self, res):
         info = res.info_host()
         self.info = {"status": int(info[0]), "first_bad_column": int(info[1]), "pinned": int(info[2]),

@@ -159,6 +159,18 @@ int fsb_residual(fsb_handle_t h, const double* A, int64_t lda, const double* b,
 int fsb_predict(fsb_handle_t h, const double* A, int64_t lda, int64_t n_rows, int32_t k,
                 const double* x, double* y, void* stream);
 
+/* ---- error analysis -------------------------------------------------------------------
+ * One pass over A giving, per group id, the sums from which Solver.error_analysis builds its
+ * MAE / RMSE / R^2 table (solvers/solver.py:108-133, 368-429): with pred = a . x, res = b - pred,
+ *   stats[g*10 + 0..9] += n, sum|res|, sum res^2, sum t, sum t^2,
+ *                         n(w != 0), sum|w res|, sum (w res)^2, sum w t, sum (w t)^2.
+ * group_id: int32[n_rows] in [0, n_groups); the caller encodes (Groups, Testing, Row_Type) into it.
+ * `stats` (n_groups*10 doubles) must be zeroed by the caller; accumulation uses atomics.
+ */
+int fsb_group_stats(fsb_handle_t h, const double* A, int64_t lda, const double* b, const double* w,
+                    const int32_t* group_id, int64_t n_rows, int32_t k, const double* x,
+                    int32_t n_groups, double* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

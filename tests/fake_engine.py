@@ -51,6 +51,16 @@ class OracleEngine:
         w[batch.row_begin:batch.row_end] = torch.from_numpy(w_)
         return A, b, w, bad
 
+    def group_stats(self, A, b, w, group_id, x, n_groups):
+        a, t, wv, g = A.numpy(), b.numpy(), w.numpy(), group_id.numpy()
+        res = t - a @ x.numpy()
+        out = np.zeros((n_groups, 10))
+        cols = [np.ones_like(t), np.abs(res), res ** 2, t, t * t, (wv != 0).astype(float), np.abs(wv * res),
+                (wv * res) ** 2, wv * t, (wv * t) ** 2]
+        for q, c in enumerate(cols):
+            np.add.at(out[:, q], g, c)
+        return torch.from_numpy(out)
+
     def predict(self, A, x):
         return torch.from_numpy(A.numpy() @ x.numpy())
 

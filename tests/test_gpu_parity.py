@@ -391,3 +391,29 @@ def test_lasso_matches_tightly_converged_sklearn(engine, ta):
     s2.perform_fit()
     aw, bw = lf.weighted_system(ta["a"], ta["b"], ta["w"])
     assert lf.lasso_objective(aw, bw, s2.fit, 1e-6) <= lf.lasso_objective(aw, bw, ta["ref_lasso_1e6"], 1e-6) * (1 + 1e-9)
+
+
+def test_group_stats_and_ta_metrics_golden(engine, ta):
+    """Device error sums -> the numbers of the reference's golden Ta_metrics.md ('*ALL', Unweighted,
+    Training, Energy: MAE 0.112787, RMSE 0.379769) and, per group, numpy on the host."""
+    from fitsnap_b200 import errors as er
+    a, b, w = ta["a"], ta["b"], ta["w"]
+    x = lf.svd_fit(a, b, w)
+    n = a.shape[0]
+    # the legacy golden arrays hold 363 energy rows, then 12672 force rows, then 2178 stress rows
+    rt = ["Energy"] * 363 + ["Force"] * 12672 + ["Stress"] * 2178
+    rng = np.random.default_rng(0)
+    grp = ["g%d" % v for v in rng.integers(0, 5, n)]
+    fs = {"Groups": grp, "Testing": [False] * n, "Row_Type": rt}
+    df = er.linear_error_analysis(engine, a, b, w, fs, x)
+    e = df.loc[("*ALL", "Unweighted", "Training", "Energy")]
+    assert abs(e["mae"] - 0.112787) < 5e-7 and abs(e["rmse"] - 0.379769) < 5e-7 and e["ncount"] == 363
+    p = lf.predictions(a, x)
+    for key in [("g1", "Force"), ("g3", "Stress"), ("g0", "Energy")]:
+        sel = np.array([g == key[0] and r == key[1] for g, r in zip(grp, rt)])
+        ref = lf.group_errors(b[sel], p[sel], w[sel])
+        for wname, pre in (("Unweighted", ""), ("weighted", "w_")):
+            row = df.loc[(key[0], wname, "Training", key[1])]
+            for m in ("mae", "rmse", "rsq"):
+                assert np.isclose(row[m], ref[pre + m], rtol=1e-9, atol=1e-13), (key, wname, m, row[m], ref[pre + m])
+            assert row["ncount"] == ref[pre + "ncount"]

@@ -83,3 +83,29 @@ def test_full_plugin_flow_matches_reference_fit(registered):
     s.error_analysis()                   # inherited from the reference's Solver (solver.py:137-435)
     assert len(s.errors) > 0
     assert s.fit.shape[0] == nc + 1      # unchanged by _offset (bzeroflag = 0)
+
+
+def test_device_error_analysis_matches_reference_table(registered):
+    """`error_analysis_device` (ten sums per group from one pass) reproduces the table the reference
+    builds through DataFrame(a) + groupby (solver.py:368-429), index and values."""
+    from fitsnap3lib.solvers.solver_factory import solver
+    rng = np.random.default_rng(11)
+    kw = dict(numtypes=1, types="Ta", twojmax="4", bzeroflag=0)
+    pt0, cfg0 = rd.make_reference_context(**kw)
+    nc = cfg0.sections["BISPECTRUM"].ncoeff
+    cfgs, blocks, vols = _configs(rng, nc, 1, n_cfg=30)
+    a, b, w, lists, cfg, pt, calc = rd.ref_scatter(cfgs, blocks, vols, use_factory=True, **kw)
+    s = solver("SVD", pt, cfg)
+    s.refine = 2
+    s.perform_fit()
+    fit = s.fit.copy()
+    s.error_analysis()                       # the reference's implementation (inherited)
+    ref = s.errors.copy()
+    s.fit = fit                              # bzeroflag = 0: _offset did not touch it
+    dev = s.error_analysis_device()
+    assert list(dev.index) == list(ref.index) and list(dev.columns) == list(ref.columns)
+    assert np.array_equal(dev["ncount"].values, ref["ncount"].values)
+    for col in ("mae", "rmse", "rsq"):
+        r, d = ref[col].values.astype(float), dev[col].values.astype(float)
+        ok = np.isclose(d, r, rtol=1e-9, atol=1e-12) | (np.isnan(d) & np.isnan(r)) | (~np.isfinite(r) & ~np.isfinite(d))
+        assert ok.all(), (col, ref[col][~ok], dev[col][~ok])
