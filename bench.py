@@ -396,7 +396,20 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX, group=group)
         dt = float(tt.item())
+        # context for the e2e number: the raw PCIe rate of this box (one pinned copy of the blocks, device-timed)
+        raw_h = torch.from_numpy(host["raw"])
+        dst = torch.empty_like(batch.raw)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dst.copy_(raw_h, non_blocking=True)
+        c0.record()
+        dst.copy_(raw_h, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_gbps = raw_h.numel() * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del dst
         e2e = {"value": world * n_rows / dt, "unit": "rows/s", "h2d_bytes_per_step": int(b_.h2d_bytes),
+               "chunks": int(getattr(b_, "chunks", 1)), "pcie_h2d_GBps": round(h2d_gbps, 2),
+               "pcie_bound_ms": round(int(b_.h2d_bytes) / (h2d_gbps * 1e9) * 1e3, 3),
                "d2h_bytes_per_step": int(8 * k + 4), "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "api": "fitsnap_b200.pipeline.LinearFitPipeline.fit_host (pinned host raw blocks -> H2D -> scatter -> "
                       "fit -> D2H coefficients)",

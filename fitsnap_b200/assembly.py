@@ -98,6 +98,22 @@ def pack_configs(engine, blocks, natoms, volumes, energies, forces, stresses, ew
     ncfg = int(natoms.shape[0])
     kraw = ncoeff * numtypes
     k = descriptor_width(ncoeff, numtypes, bzeroflag)
+    up = engine.to_device
+    n_raw = 7 * ncfg + 3 * int(natoms.sum(dtype=np.int64))
+
+    # the descriptor blocks are >99 % of the bytes: put that copy on the wire first and do the
+    # bookkeeping below while it is in flight
+    if isinstance(blocks, np.ndarray) and blocks.ndim == 2:
+        raw = np.ascontiguousarray(blocks, dtype=np.float64)
+    else:
+        raw_off0 = np.zeros(ncfg + 1, dtype=np.int64)
+        np.cumsum(7 + 3 * natoms.astype(np.int64), out=raw_off0[1:])
+        raw = np.empty((n_raw, kraw + 1), dtype=np.float64)
+        for c, blk in enumerate(blocks):
+            raw[raw_off0[c]:raw_off0[c + 1]] = blk
+    assert raw.shape == (n_raw, kraw + 1), (raw.shape, n_raw, kraw + 1)
+    raw_dev = up(raw)
+
     raw_rows = 7 + 3 * natoms.astype(np.int64)
     raw_off = np.zeros(ncfg + 1, dtype=np.int64)
     np.cumsum(raw_rows, out=raw_off[1:])
@@ -106,13 +122,6 @@ def pack_configs(engine, blocks, natoms, volumes, energies, forces, stresses, ew
     np.cumsum(out_rows, out=out_off[1:])
     out_off += int(first_row)
 
-    if isinstance(blocks, np.ndarray) and blocks.ndim == 2:
-        raw = np.ascontiguousarray(blocks, dtype=np.float64)
-    else:
-        raw = np.empty((int(raw_off[-1]), kraw + 1), dtype=np.float64)
-        for c, blk in enumerate(blocks):
-            raw[raw_off[c]:raw_off[c + 1]] = blk
-    assert raw.shape == (int(raw_off[-1]), kraw + 1), (raw.shape, raw_off[-1], kraw + 1)
     if isinstance(forces, np.ndarray):
         fcat = np.ascontiguousarray(forces, dtype=np.float64).reshape(-1)
     else:
@@ -125,16 +134,16 @@ def pack_configs(engine, blocks, natoms, volumes, energies, forces, stresses, ew
     b2j = np.ascontiguousarray(blank2j, dtype=np.float64)
     assert b2j.shape == (k,), (b2j.shape, k)
 
-    row_cfg = np.repeat(np.arange(ncfg, dtype=np.int32), out_rows)
-    up = engine.to_device
-    host = dict(raw=raw, volume=np.asarray(volumes, dtype=np.float64), energy=np.asarray(energies, dtype=np.float64),
+    host = dict(volume=np.asarray(volumes, dtype=np.float64), energy=np.asarray(energies, dtype=np.float64),
                 forces=fcat, stress=st, eweight=np.asarray(eweights, dtype=np.float64),
                 fweight=np.asarray(fweights, dtype=np.float64), vweight=np.asarray(vweights, dtype=np.float64),
                 type_fraction=tf, blank2j=b2j)
     dev = {name: up(arr) for name, arr in host.items()}
-    nbytes = sum(a.nbytes for a in host.values()) + raw_off.nbytes + out_off.nbytes + natoms.nbytes + row_cfg.nbytes
+    dev["raw"] = raw_dev
+    # row -> configuration map: left to the kernel (binary search in out_row_off), nothing to upload
+    nbytes = raw.nbytes + sum(a.nbytes for a in host.values()) + raw_off.nbytes + out_off.nbytes + natoms.nbytes
     return ConfigBatch(raw_row_off=up(raw_off, dtype=torch.int64), out_row_off=up(out_off, dtype=torch.int64),
                        natoms=up(natoms, dtype=torch.int32), ncfg=ncfg, numtypes=int(numtypes), ncoeff=int(ncoeff),
                        flags=make_flags(energy, force, stress, bzeroflag, scrub_nonfinite), k=k,
-                       row_begin=int(out_off[0]), row_end=int(out_off[-1]), row_cfg=up(row_cfg, dtype=torch.int32),
+                       row_begin=int(out_off[0]), row_end=int(out_off[-1]), row_cfg=None,
                        h2d_bytes=int(nbytes), **dev)

@@ -33,6 +33,12 @@ int fsb_launch_group_stats(const fsb_context* h, const double* A, int64_t lda, c
                            const int32_t* gid, int64_t n_rows, int k, const double* x, int n_groups, double* stats,
                            cudaStream_t s);
 
+size_t fsb_pinv_bytes_impl(int k);
+int fsb_launch_pinv_factor(const fsb_context* h, const double* gaug, int k, double rcond, void* buf, size_t bytes,
+                           int32_t* info, cudaStream_t s);
+int fsb_launch_pinv_apply(const void* buf, int k, const double* rhs, int64_t rhs_stride, const double* x_in,
+                          double* x_out, cudaStream_t s);
+
 static thread_local char g_cuda_err[512] = "";
 
 void fsb_note_cuda_error(cudaError_t e, const char* where) {
@@ -151,6 +157,23 @@ int fsb_factor_solve(fsb_handle_t h, const void* factor, int32_t k, const double
   if (!h || !factor || k < 1 || k > FSB_MAX_K || !rhs || rhs_stride < 1 || !x_out)
     return FSB_ERR_INVALID_ARGUMENT;
   return fsb_launch_factor_solve(h, factor, k, rhs, rhs_stride, alpha, x_in, x_out, (cudaStream_t)stream);
+}
+
+size_t fsb_pinv_bytes(fsb_handle_t h, int32_t k) {
+  if (!h || k < 1) return 0;
+  return fsb_pinv_bytes_impl(k);
+}
+
+int fsb_pinv_factor(fsb_handle_t h, const double* gaug, int32_t k, double rcond, void* pinv, size_t pinv_bytes,
+                    int32_t* info, void* stream) {
+  if (!h || !gaug || k < 1 || k > FSB_MAX_K || !pinv || !info || !(rcond >= 0.0)) return FSB_ERR_INVALID_ARGUMENT;
+  return fsb_launch_pinv_factor(h, gaug, k, rcond, pinv, pinv_bytes, info, (cudaStream_t)stream);
+}
+
+int fsb_pinv_apply(fsb_handle_t h, const void* pinv, int32_t k, const double* rhs, int64_t rhs_stride,
+                   const double* x_in, double* x_out, void* stream) {
+  if (!h || !pinv || k < 1 || k > FSB_MAX_K || !rhs || rhs_stride < 1 || !x_out) return FSB_ERR_INVALID_ARGUMENT;
+  return fsb_launch_pinv_apply(pinv, k, rhs, rhs_stride, x_in, x_out, (cudaStream_t)stream);
 }
 
 int fsb_lasso(fsb_handle_t h, const double* gaug, int32_t k, int64_t n_train, double alpha, int32_t max_iter,

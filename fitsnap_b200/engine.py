@@ -32,6 +32,13 @@ class Factor:
 
 
 @dataclass
+class PinvFactor:
+    buf: torch.Tensor
+    info: torch.Tensor
+    k: int
+
+
+@dataclass
 class FitResult:
     x: torch.Tensor                 # (k,) device fp64
     gaug: torch.Tensor              # (k+1, k+1) device fp64, already all-reduced
@@ -146,6 +153,26 @@ class Engine:
         self.launch_count += 1
         return x
 
+    def pinv_factor(self, gaug, rcond=None):
+        """G^+ through a Jacobi eigendecomposition (minimum-norm fallback, see csrc/pinv.cu)."""
+        k = gaug.shape[0] - 1
+        if rcond is None:
+            rcond = k * 2.220446049250313e-16
+        nbytes = self.lib.fsb_pinv_bytes(self._h, k)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        info = torch.zeros(2, dtype=torch.int32, device=self.device)
+        _cabi.check("fsb_pinv_factor", self.lib.fsb_pinv_factor(self._h, _ptr(gaug), k, float(rcond), _ptr(buf), nbytes,
+                                                                 _ptr(info), self._stream()))
+        self.launch_count += 2
+        return PinvFactor(buf, info, k)
+
+    def pinv_apply(self, pf, rhs, rhs_stride=1, x_in=None):
+        x = torch.empty(pf.k, dtype=torch.float64, device=self.device)
+        _cabi.check("fsb_pinv_apply", self.lib.fsb_pinv_apply(self._h, _ptr(pf.buf), pf.k, _ptr(rhs), int(rhs_stride),
+                                                               _ptr(x_in), _ptr(x), self._stream()))
+        self.launch_count += 1
+        return x
+
     def lasso(self, gaug, n_train, alpha, max_iter=2000, tol=1e-12):
         """Coordinate descent on the reduced problem (lasso.py:25-29 objective)."""
         k = gaug.shape[0] - 1
@@ -221,7 +248,7 @@ def _all_reduce(t, group):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
-def fit_rows(engine, A, b, w, testing=None, alpha=0.0, refine=2, group=None, diagnostics=True):
+def fit_rows(engine, A, b, w, testing=None, alpha=0.0, refine=2, group=None, diagnostics=True, gaug=None):
     """Weighted least squares / ridge on this rank's row shard (`engine` = `Engine`, or any object
     with gram/factor/solve/residual -- the CPU gloo tests drive this function with a stand-in).
 
@@ -233,7 +260,8 @@ def fit_rows(engine, A, b, w, testing=None, alpha=0.0, refine=2, group=None, dia
     Every rank ends with the same x (replicated solve, no broadcast).
     """
     start = getattr(engine, "launch_count", 0)
-    gaug = engine.gram(A, b, w, testing)
+    if gaug is None:                 # a caller that streamed the rows in has accumulated it already
+        gaug = engine.gram(A, b, w, testing)
     _all_reduce(gaug, group)
     k = gaug.shape[0] - 1
     f = engine.factor(gaug, alpha)
@@ -248,6 +276,25 @@ def fit_rows(engine, A, b, w, testing=None, alpha=0.0, refine=2, group=None, dia
         x = x_new
     return FitResult(x=x, gaug=gaug, info=f.info, last_correction=last,
                      launches=getattr(engine, "launch_count", 0) - start, extra={"factor": f})
+
+
+def fit_rows_min_norm(engine, A, b, w, testing, gaug, refine=3, group=None, rcond=None):
+    """Minimum-norm least squares for a rank-deficient system (what gelsd returns, svd.py:54):
+    x0 = G^+ c, then x += G^+ aw^T (bw - aw x) with the residual streamed from A.  `gaug` is the
+    (already all-reduced) augmented Gram of `fit_rows`."""
+    start = getattr(engine, "launch_count", 0)
+    k = gaug.shape[0] - 1
+    pf = engine.pinv_factor(gaug, rcond)
+    x = engine.pinv_apply(pf, gaug[:, k], rhs_stride=k + 1)
+    last = None
+    for _ in range(int(refine)):
+        g = engine.residual(A, b, w, testing, x)
+        _all_reduce(g, group)
+        x_new = engine.pinv_apply(pf, g, x_in=x)
+        last = (x_new - x).abs().max() / x_new.abs().max().clamp_min(1e-300)
+        x = x_new
+    return FitResult(x=x, gaug=gaug, info=pf.info, last_correction=last,
+                     launches=getattr(engine, "launch_count", 0) - start, extra={"pinv": pf, "min_norm": True})
 
 
 def refine_rows(engine, A, b, w, testing, res, group=None):

@@ -10,8 +10,10 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from types import SimpleNamespace
+
 from .assembly import ConfigBatch, pack_configs
-from .engine import Engine, FitResult, default_engine
+from .engine import Engine, FitResult, default_engine, fit_rows
 
 
 class LinearFitPipeline:
@@ -39,9 +41,22 @@ class LinearFitPipeline:
         res.extra.update(A=A, b=b, w=w, nonfinite=bad)
         return res
 
+    #: raw bytes above which fit_host streams the blocks in chunks (copy of chunk c+1 overlaps the
+    #: scatter + partial Gram of chunk c); below it one copy + one launch of each kernel is faster
+    pipeline_min_bytes = 64 << 20
+    pipeline_chunks = 8
+
     def fit_host(self, blocks, natoms, volumes, energies, forces, stresses, eweights, fweights, vweights,
-                 type_fraction=None, testing=None):
+                 type_fraction=None, testing=None, chunks=None):
         """Host buffers in, host coefficients out (H2D of the blocks and D2H of x included)."""
+        natoms = np.asarray(natoms, dtype=np.int32)
+        if chunks is None:
+            raw_bytes = (7 * len(natoms) + 3 * int(natoms.sum(dtype=np.int64))) * (self.ncoeff * self.numtypes + 1) * 8
+            chunks = self.pipeline_chunks if raw_bytes >= self.pipeline_min_bytes else 1
+        chunks = max(1, min(int(chunks), len(natoms)))
+        if chunks > 1 and isinstance(blocks, np.ndarray) and isinstance(forces, np.ndarray):
+            return self._fit_host_streamed(blocks, natoms, volumes, energies, forces, stresses, eweights, fweights,
+                                           vweights, type_fraction, testing, chunks)
         batch = self.pack(blocks, natoms, volumes, energies, forces, stresses, eweights, fweights, vweights,
                           type_fraction)
         T = None
@@ -52,3 +67,68 @@ class LinearFitPipeline:
         if int(res.extra["nonfinite"].item()) and not self.scrub:
             raise ValueError("Nan in computed data")     # lammps_snap.py:426-428
         return x, res, batch
+
+    def _fit_host_streamed(self, raw, natoms, volumes, energies, forces, stresses, eweights, fweights, vweights,
+                           type_fraction, testing, chunks):
+        """Chunked upload on a side stream; each chunk is scattered into its rows of (A, b, w) and its
+        rows' Gram is added to the running sum while the next chunk is on the wire.  After the last
+        chunk only 1/chunks of the scatter + Gram, the factorisation and the refinement passes remain."""
+        eng = self.engine
+        ncfg = len(natoms)
+        e, f, s = self.rows
+        raw_rows = 7 + 3 * natoms.astype(np.int64)
+        raw_off = np.concatenate([[0], np.cumsum(raw_rows)])
+        out_rows = int(e) + 3 * natoms.astype(np.int64) * int(f) + 6 * int(s)
+        out_off = np.concatenate([[0], np.cumsum(out_rows)])
+        atom_off = np.concatenate([[0], np.cumsum(natoms.astype(np.int64))])
+        # chunk boundaries: equal shares of raw rows, cut at configuration boundaries
+        targets = raw_off[-1] * np.arange(1, chunks) / chunks
+        cuts = np.unique(np.concatenate([[0], np.searchsorted(raw_off, targets, side="left"), [ncfg]]))
+        k = self.blank2j.shape[0]
+        n_out = int(out_off[-1])
+        dev = eng.device
+        A = torch.empty((n_out, k), dtype=torch.float64, device=dev)
+        b = torch.empty(n_out, dtype=torch.float64, device=dev)
+        w = torch.empty(n_out, dtype=torch.float64, device=dev)
+        T = None
+        if testing is not None:
+            T = eng.to_device(np.ascontiguousarray(testing, dtype=np.uint8), dtype=torch.uint8)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        copy_stream = self._copy_stream
+        main = torch.cuda.current_stream(dev)
+        copy_stream.wait_stream(main)                 # A/b/w allocations and earlier work are ordered
+        forces = np.ascontiguousarray(forces, dtype=np.float64).reshape(-1)
+        stresses = np.asarray(stresses, dtype=np.float64).reshape(ncfg, 9)
+        tf = None if type_fraction is None else np.asarray(type_fraction, dtype=np.float64).reshape(ncfg, -1)
+        sl = lambda arr, c0, c1: np.asarray(arr, dtype=np.float64)[c0:c1]
+        gaug = None
+        bad = None
+        batches = []
+        h2d = 0
+        for c0, c1 in zip(cuts[:-1], cuts[1:]):
+            c0, c1 = int(c0), int(c1)
+            with torch.cuda.stream(copy_stream):
+                batch = self.pack(raw[raw_off[c0]:raw_off[c1]], natoms[c0:c1], sl(volumes, c0, c1), sl(energies, c0, c1),
+                                  forces[3 * atom_off[c0]:3 * atom_off[c1]], stresses[c0:c1], sl(eweights, c0, c1),
+                                  sl(fweights, c0, c1), sl(vweights, c0, c1), None if tf is None else tf[c0:c1],
+                                  first_row=int(out_off[c0]))
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            main.wait_event(ev)
+            batches.append(batch)
+            h2d += batch.h2d_bytes
+            _, _, _, bad_c = eng.scatter(batch, A, b, w, lda=k)
+            r0, r1 = int(out_off[c0]), int(out_off[c1])
+            g_c = eng.gram(A[r0:r1], b[r0:r1], w[r0:r1], None if T is None else T[r0:r1])
+            gaug = g_c if gaug is None else gaug.add_(g_c)
+            bad = bad_c if bad is None else bad.add_(bad_c)
+        res = fit_rows(eng, A, b, w, T, alpha=self.alpha, refine=self.refine, group=self.group, diagnostics=False,
+                       gaug=gaug)
+        res.extra.update(A=A, b=b, w=w, nonfinite=bad, batches=batches)
+        x = res.coefficients()          # D2H + sync (the chunk buffers are alive until here)
+        if int(bad.item()) and not self.scrub:
+            raise ValueError("Nan in computed data")     # lammps_snap.py:426-428
+        summary = SimpleNamespace(ncfg=ncfg, k=k, row_begin=0, row_end=n_out, n_rows_out=n_out, h2d_bytes=int(h2d),
+                                  chunks=len(batches))
+        return x, res, summary

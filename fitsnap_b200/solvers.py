@@ -46,6 +46,8 @@ class LinearSolverBase:
     #: refinement rounds: "auto" iterates until the correction stalls (one host sync per round)
     refine = "auto"
     max_refine = 10
+    #: rank-deficient least squares (alpha = 0): reproduce lstsq's minimum-norm answer through G^+
+    min_norm_fallback = True
 
     def __init__(self, name, pt, config, linear=True):
         self.name = name
@@ -146,6 +148,11 @@ class LinearSolverBase:
         res = self._run_fit(A, B, W, T, self._alpha())
         self.last_result = res
         self._check_info(res)
+        if self.info["status"] != 0 and self._alpha() == 0.0 and self.min_norm_fallback:
+            # linearly dependent columns: lstsq (svd.py:54) returns the minimum-norm solution
+            res = _engine.fit_rows_min_norm(self._engine(), A, B, W, T, res.gaug, refine=3, group=self.process_group)
+            self.last_result = res
+            self.info["min_norm_rank"] = int(res.info[0].item())
         self.fit = res.coefficients()
 
     def error_analysis_device(self, a=None, b=None, w=None, fs_dict=None):

@@ -136,6 +136,22 @@ int fsb_factor_solve(fsb_handle_t h, const void* factor, int32_t k, const double
                      int64_t rhs_stride, double alpha, const double* x_in, double* x_out,
                      void* stream);
 
+/* ---- minimum-norm fallback (rank-deficient systems) -----------------------------------
+ * scipy.linalg.lstsq(aw, bw, 1e-13) (solvers/svd.py:54, gelsd) returns the MINIMUM-NORM solution
+ * when columns are linearly dependent; fsb_factor reports such a system in info[] (status 1).
+ * fsb_pinv_factor builds G^+ = V diag(1/lambda_i | lambda_i > rcond * lambda_max) V^T from a Jacobi
+ * eigendecomposition of the (un-equilibrated) Gram in `gaug`; fsb_pinv_apply does
+ *   x_out = (x_in ? x_in : 0) + G^+ rhs,
+ * i.e. the initial solve (rhs = aw^T bw) and each refinement step (rhs = fsb_residual output).
+ * info[0] = numerical rank, info[1] = Jacobi sweeps (device int32[2]).  rcond acts on eigenvalues
+ * of G (squared singular values); k * 2.2e-16 is the resolution of a Gram formed in fp64.
+ */
+size_t fsb_pinv_bytes(fsb_handle_t h, int32_t k);
+int fsb_pinv_factor(fsb_handle_t h, const double* gaug, int32_t k, double rcond, void* pinv,
+                    size_t pinv_bytes, int32_t* info, void* stream);
+int fsb_pinv_apply(fsb_handle_t h, const void* pinv, int32_t k, const double* rhs, int64_t rhs_stride,
+                   const double* x_in, double* x_out, void* stream);
+
 /* ---- LASSO on the reduced problem ----------------------------------------------------
  * Replaces sklearn Lasso(alpha, fit_intercept=False, max_iter).fit(aw, bw) as called at
  * solvers/lasso.py:25-29: argmin 1/(2 n_train) |bw - aw x|^2 + alpha |x|_1, by cyclic coordinate

@@ -263,6 +263,46 @@ def test_rank_deficient_duplicate_column_is_reported(engine):
     assert abs(np.linalg.norm(a @ x - b) - r_ref) < 1e-9 * r_ref
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,k,dups", [(500, 10, [(7, 2)]), (3000, 150, [(20, 3), (149, 77), (60, 3)])])
+def test_min_norm_fallback_matches_lstsq(engine, n, k, dups):
+    """Linearly dependent columns: lstsq(aw, bw, 1e-13) (svd.py:54) returns the minimum-norm
+    solution; the G^+ path (Jacobi eigendecomposition + refinement) reproduces it."""
+    from fitsnap_b200 import engine as eng
+    rng = np.random.default_rng(11)
+    a = rng.standard_normal((n, k)) * np.logspace(0, 2, k)
+    for dst, src in dups:
+        a[:, dst] = a[:, src]
+    a[:, 5] = 0.0                                                  # an all-zero column as well
+    b, w = rng.standard_normal(n), rng.uniform(0.5, 2.0, n)
+    x_ref = lf.svd_fit(a, b, w)
+    A, B, W = engine.to_device(a), engine.to_device(b), engine.to_device(w)
+    res = eng.fit_rows(engine, A, B, W, None, alpha=0.0, refine=0)
+    assert res.info_host()[0] == 1
+    mn = eng.fit_rows_min_norm(engine, A, B, W, None, res.gaug, refine=3)
+    x = mn.coefficients()
+    ndep = len({d for d, _ in dups})
+    assert int(mn.info[0].item()) == k - 1 - ndep                  # numerical rank
+    assert x[5] == 0.0
+    for dst, src in dups:
+        assert abs(x[dst] - x[src]) < 1e-10 * abs(x[src])           # min norm splits evenly
+    assert lf.coeff_rel_err(x, x_ref)[0] < 1e-10
+
+
+@pytest.mark.gpu
+def test_svd_mirror_uses_min_norm_for_dependent_columns(engine):
+    from types import SimpleNamespace
+    from fitsnap_b200.solvers import SVD
+    rng = np.random.default_rng(12)
+    a = rng.standard_normal((800, 12))
+    a[:, 9] = a[:, 1]
+    b, w = rng.standard_normal(800), np.ones(800)
+    s = SVD("SVD", _pt(a, b, w), SimpleNamespace(sections={}))
+    s.perform_fit()
+    assert s.info["status"] == 1 and s.info["min_norm_rank"] == 11
+    assert lf.coeff_rel_err(s.fit, lf.svd_fit(a, b, w))[0] < 1e-10
+
+
 # ------------------------------------------------------------------------------- plugin mirror
 def _pt(a, b, w, testing=None):
     from types import SimpleNamespace
@@ -342,6 +382,28 @@ def test_pipeline_fit_host_raises_on_nan(engine):
     with pytest.raises(ValueError):
         pipe.fit_host(raw, g["natoms"], g["volume"], g["energy"], g["forces"], g["stress"], g["eweight"],
                       g["fweight"], g["vweight"], None)
+
+
+@pytest.mark.parametrize("tag,chunks", [("snap_b0_efs", 3), ("snap_b1_efs", 50), ("pace_b0_efs", 2)])
+def test_pipeline_streamed_upload_equals_one_shot(engine, tag, chunks):
+    """fit_host with the chunked (copy/compute overlapped) upload assembles the same rows, bit for bit,
+    and gives the same coefficients as the single-copy path and the reference rows' ridge fit."""
+    from fitsnap_b200.pipeline import LinearFitPipeline
+    g = load_golden("scatter_%s.npz" % tag)
+    pipe = LinearFitPipeline(int(g["numtypes"]), int(g["ncoeff"]), bool(int(g["bzeroflag"])), g["blank2j"],
+                             alpha=1e4, engine=engine, scrub_nonfinite=tag.startswith("pace"))
+    tf = None if int(g["bzeroflag"]) else g["type_fraction"]
+    args = (g["raw"], g["natoms"], g["volume"], g["energy"], g["forces"], g["stress"], g["eweight"], g["fweight"],
+            g["vweight"], tf)
+    x1, r1, _ = pipe.fit_host(*args, chunks=1)
+    xs, rs, summ = pipe.fit_host(*args, chunks=chunks)
+    assert summ.chunks >= 2
+    assert np.array_equal(rs.extra["A"].cpu().numpy(), g["ref_a"])
+    assert np.array_equal(rs.extra["b"].cpu().numpy(), g["ref_b"])
+    assert np.array_equal(rs.extra["w"].cpu().numpy(), g["ref_w"])
+    x_ref = lf.ridge_fit_exact(g["ref_a"], g["ref_b"], g["ref_w"], 1e4)     # two of the cases are rank deficient
+    assert lf.coeff_rel_err(xs, x_ref)[0] < 1e-9 and lf.coeff_rel_err(x1, x_ref)[0] < 1e-9
+    assert lf.coeff_rel_err(xs, x1)[0] < 1e-10
 
 
 @pytest.mark.parametrize("tag", ["snap_b0_efs", "pace_b1_efs"])
