@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", LIB_
 
 # flags / info indices mirrored from the header
 ROWS_ENERGY, ROWS_FORCE, ROWS_STRESS, BZEROFLAG, SCRUB_NONFINITE = 1, 2, 4, 8, 16
+GRAM_AUTO, GRAM_FP64, GRAM_INT8 = 0, 1, 2
 INFO_STATUS, INFO_FIRST_BAD_COLUMN, INFO_NUM_PINNED, INFO_NUM_DEFICIENT, INFO_LEN = 0, 1, 2, 3, 8
 
 # every symbol include/fitsnap_b200.h declares: name -> (restype, argtypes)
@@ -28,6 +29,8 @@ SIGNATURES = {
     "fsb_sm_count": (c_int, [c_void_p, POINTER(c_int)]),
     "fsb_scatter": (c_int, [c_void_p, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                             c_int32, c_int32, c_int32, c_int32, _P, c_int64, _P, _P, c_int64, _P, _P, c_void_p]),
+    "fsb_set_gram_path": (c_int, [c_void_p, c_int32]),
+    "fsb_get_gram_path": (c_int, [c_void_p, c_int64, c_int32, POINTER(c_int32)]),
     "fsb_gram_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int32]),
     "fsb_gram": (c_int, [c_void_p, _P, c_int64, _P, _P, _P, c_int64, c_int32, _P, _P, c_size_t, c_void_p]),
     "fsb_factor_bytes": (c_size_t, [c_void_p, c_int32]),

@@ -21,7 +21,7 @@ LIB_DIR = os.path.join(PKG, "_lib")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB_PATH = os.path.join(LIB_DIR, "libfitsnap_b200.so")
 
-SOURCES = ["fsb_api.cu", "gram.cu", "solve.cu", "stream_ops.cu", "lasso.cu", "gram_small.cu", "gram_tma.cu", "pinv.cu"]
+SOURCES = ["fsb_api.cu", "gram.cu", "solve.cu", "stream_ops.cu", "lasso.cu", "gram_small.cu", "gram_tma.cu", "pinv.cu", "gram_i8.cu"]
 HEADERS = ["fsb_common.cuh", os.path.join(ROOT, "include", "fitsnap_b200.h")]
 
 NVCC_FLAGS = [

@@ -3,6 +3,7 @@
 #include "fsb_common.cuh"
 #include <string.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <new>
 
 // launchers (gram.cu, solve.cu, stream_ops.cu)
@@ -25,6 +26,9 @@ int fsb_launch_scatter(const fsb_context* h, const double* raw, const int64_t* r
                        const double* type_fraction, const double* blank2j, int ncfg, int numtypes,
                        int ncoeff, int flags, double* A, int64_t lda, double* b, double* w,
                        int32_t* nonfinite, const int32_t* row_cfg, int64_t n_rows_hint, cudaStream_t s);
+
+bool fsb_gram_i8_available();
+int fsb_gram_path_for(const fsb_context* h, int64_t n_rows, int k);
 
 int fsb_launch_lasso(const fsb_context* h, const double* gaug, int k, double n_train, double alpha, int max_iter,
                      double tol, double* x_out, int32_t* info, cudaStream_t s);
@@ -88,6 +92,11 @@ int fsb_create(fsb_handle_t* out, int device) {
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   h->smem_optin = prop.sharedMemPerBlockOptin;
+  h->gram_path = FSB_GRAM_AUTO;
+  if (const char* e = getenv("FSB_GRAM_PATH")) {
+    if (!strcmp(e, "fp64")) h->gram_path = FSB_GRAM_FP64;
+    else if (!strcmp(e, "int8")) h->gram_path = FSB_GRAM_INT8;
+  }
   *out = h;
   return FSB_OK;
 }
@@ -123,6 +132,19 @@ int fsb_scatter(fsb_handle_t h, const double* raw, const int64_t* raw_row_off, c
   return fsb_launch_scatter(h, raw, raw_row_off, out_row_off, natoms, volume, energy, forces, stress, eweight,
                             fweight, vweight, type_fraction, blank2j, ncfg, numtypes, ncoeff, flags, A, lda, b,
                             w, nonfinite, row_cfg, n_rows_out, (cudaStream_t)stream);
+}
+
+int fsb_set_gram_path(fsb_handle_t h, int32_t path) {
+  if (!h || path < FSB_GRAM_AUTO || path > FSB_GRAM_INT8) return FSB_ERR_INVALID_ARGUMENT;
+  if (path == FSB_GRAM_INT8 && !fsb_gram_i8_available()) return FSB_ERR_UNSUPPORTED;
+  h->gram_path = path;
+  return FSB_OK;
+}
+
+int fsb_get_gram_path(fsb_handle_t h, int64_t n_rows, int32_t k, int32_t* path) {
+  if (!h || !path || k < 1) return FSB_ERR_INVALID_ARGUMENT;
+  *path = fsb_gram_path_for(h, n_rows, k);
+  return FSB_OK;
 }
 
 size_t fsb_gram_workspace_bytes(fsb_handle_t h, int64_t n_rows, int32_t k) {

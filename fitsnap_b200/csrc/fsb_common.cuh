@@ -9,6 +9,7 @@ struct fsb_context {
   int device;
   int sm_count;
   size_t smem_optin;   // max dynamic shared memory per block (opt-in)
+  int gram_path;       // FSB_GRAM_AUTO / FSB_GRAM_FP64 / FSB_GRAM_INT8 (fsb_set_gram_path)
 };
 
 // thread-local last CUDA error text (fsb_last_cuda_error)
@@ -42,6 +43,10 @@ constexpr int FSB_GT = 128;          // super-tile edge (columns of A)
 constexpr int FSB_GRCH = 32;         // rows of A per shared-memory pipeline stage
 constexpr int FSB_GLDS = FSB_GT + 4; // smem row pitch in doubles: == 4 (mod 16) -> conflict-free DMMA fragment loads
 constexpr int FSB_GTHREADS = 512;    // 16 warps, each owning a 32x32 sub-tile (4x4 DMMA 8x8 blocks)
+
+// FSB_GRAM_AUTO switches to the int8 tcgen05 Gram from this shape on (gram.cu: fsb_gram_path_for)
+constexpr int FSB_I8_AUTO_MIN_COLS = 1 << 30;   // not enabled by default yet
+constexpr int64_t FSB_I8_AUTO_MIN_ROWS = 65536;
 
 // Cholesky panel width
 constexpr int FSB_NB = 64;

@@ -328,6 +328,22 @@ static size_t waug_bytes(int64_t n_rows, int k) {
   return (k + 1 <= FSB_GT) ? 0 : align256((size_t)(n_rows > 0 ? n_rows : 1) * (size_t)fsb_gram_tma_ldw(k) * sizeof(double));
 }
 
+// exact-integer Gram on the int8 tcgen05 tensor cores (gram_i8.cu)
+bool fsb_gram_i8_available();
+size_t fsb_gram_i8_ws_bytes(int64_t n_rows, int k);
+int fsb_launch_gram_i8(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* weff,
+                       int64_t n_rows, int k, double* gaug, void* ws, size_t ws_bytes, cudaStream_t s);
+
+// FSB_GRAM_AUTO: the int8 path pays a conversion pass (~100 integer operations per matrix element) and
+// wins once the contraction dominates it: wide matrices with enough rows to fill the machine.
+int fsb_gram_path_for(const fsb_context* h, int64_t n_rows, int k) {
+  if (h->gram_path == FSB_GRAM_INT8) return fsb_gram_i8_available() ? FSB_GRAM_INT8 : FSB_GRAM_FP64;
+  if (h->gram_path == FSB_GRAM_FP64) return FSB_GRAM_FP64;
+  if (k + 1 >= FSB_I8_AUTO_MIN_COLS && n_rows >= FSB_I8_AUTO_MIN_ROWS && fsb_gram_i8_available())
+    return FSB_GRAM_INT8;
+  return FSB_GRAM_FP64;
+}
+
 static GramPlan effective_plan(const fsb_context* h, int64_t n_rows, int k) {
   GramPlan pl = plan_gram(h, n_rows, k);
   if (use_small(k)) {
@@ -342,6 +358,8 @@ static size_t partial_bytes(const GramPlan& pl) {
 }
 
 size_t fsb_gram_ws_bytes(const fsb_context* h, int64_t n_rows, int k) {
+  if (fsb_gram_path_for(h, n_rows, k) == FSB_GRAM_INT8)
+    return align256((size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double)) + fsb_gram_i8_ws_bytes(n_rows, k);
   GramPlan pl = effective_plan(h, n_rows, k);
   // split-K partials + masked weight vector (test mask given) + pre-weighted copy (wide matrices)
   return align256(partial_bytes(pl)) + align256((size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double)) +
@@ -351,6 +369,17 @@ size_t fsb_gram_ws_bytes(const fsb_context* h, int64_t n_rows, int k) {
 int fsb_launch_gram(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* w,
                     const uint8_t* testing, int64_t n_rows, int k, double* gaug, void* ws, size_t ws_bytes,
                     cudaStream_t s) {
+  if (fsb_gram_path_for(h, n_rows, k) == FSB_GRAM_INT8) {
+    const size_t wbytes = align256((size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double));
+    if (ws_bytes < wbytes + fsb_gram_i8_ws_bytes(n_rows, k)) return FSB_ERR_WORKSPACE_TOO_SMALL;
+    const double* weff8 = w;
+    if (testing && n_rows > 0) {
+      mask_weights_kernel<<<(unsigned)fsb_ceil_div(n_rows, 256), 256, 0, s>>>(w, testing, n_rows, (double*)ws);
+      FSB_LAUNCH_CHECK("mask_weights_kernel");
+      weff8 = (const double*)ws;
+    }
+    return fsb_launch_gram_i8(h, A, lda, b, weff8, n_rows, k, gaug, (char*)ws + wbytes, ws_bytes - wbytes, s);
+  }
   GramPlan pl = effective_plan(h, n_rows, k);
   const size_t off_w = align256(partial_bytes(pl));
   const size_t off_waug = off_w + align256((size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double));

@@ -1,0 +1,634 @@
+// K2+K3+K4 on the 5th-generation tensor cores: exact-integer Gram through int8 tcgen05.mma.
+//
+// tcgen05.mma has no f64 kind, and the fit needs a Gram that is good to ~1e-15 (cond(G) = cond(Aw)^2),
+// so the fp64 contraction  G = [Aw|bw]^T [Aw|bw]  is recast as EXACT integer arithmetic that the int8
+// tensor cores can do (Ozaki scheme II: Chinese remainder theorem instead of mantissa slices):
+//
+//   per slab of <= 2^18 rows
+//   1. i8_colmax_kernel   m_c = max_r |fl(w_r a_rc)|  (augmented column c = k holds w_r b_r).  One HBM pass.
+//   2. i8_convert_kernel  q_rc = rint(fl(w_r a_rc) * 2^e_c), e_c = BETA-1-ilogb(m_c), an integer of at most
+//                         BETA <= 53 bits: the fp64 value itself when the column maximum has that exponent,
+//                         an absolute truncation at m_c 2^-BETA otherwise (what an fp64 dot product keeps of
+//                         it anyway).  For 16 pairwise coprime moduli p_t <= 256 it writes the symmetric
+//                         residues q mod p_t as int8 planes  R_t[c][r]  (row index contiguous: both MMA
+//                         operands become K-major).  q is split into its 7 low bytes + sign and two
+//                         dp4a instructions per modulus fold them with the byte weights 256^i mod p_t.
+//   3. i8_gemm_kernel     for every modulus and every 128 x 256 tile of the lower triangle:
+//                         C_t = R_t^T R_t  with tcgen05.mma.kind::i8 (M128 N256 K32, int32 accumulators in
+//                         TMEM, operands TMA-loaded with 128-byte swizzle into a 4-stage mbarrier ring; one
+//                         elected thread issues the MMAs, one the TMA loads, four warps drain TMEM).  A unit
+//                         covers <= 2^16 rows, so |C_t| <= 2^16 * 128^2 = 2^30 never wraps.  Accumulators are
+//                         added into an int64 table with integer atomics (exact, order-independent).
+//   4. i8_crt_kernel      reduces the table mod p_t, rebuilds the exact integer G'_ij = sum_r q_ri q_rj
+//                         (|G'| <= 2^18 2^106 < P/2 = 2^124.4) by Garner's mixed-radix algorithm in 128-bit
+//                         integers, rounds ONCE to fp64, scales by 2^-(e_i+e_j) and adds the slab into gaug.
+//
+// The result is the correctly rounded Gram of the quantised slab: independent of summation order, tile
+// shape and GPU count, at least as accurate normwise as the DMMA path (tests/test_gpu_parity.py).
+// References: solvers/svd.py:35-53, solvers/ridge.py:28-43 (the products this replaces).
+#include "fsb_common.cuh"
+#include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
+
+namespace {
+
+constexpr int NMOD = 16;
+constexpr int BM = 128;                 // tile rows   (columns of A, operand "A" of the MMA)
+constexpr int BN = 256;                 // tile columns (columns of A, operand "B" of the MMA)
+constexpr int BK = 128;                 // rows of the design matrix per pipeline stage (bytes of K per operand row)
+constexpr int UK = 32;                  // K of one kind::i8 MMA
+constexpr int NST = 4;
+constexpr int A_BYTES = BM * BK;        // 16 KB
+constexpr int B_BYTES = BN * BK;        // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_THREADS = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int TMEM_COLS = 256;
+constexpr int64_t SLAB_ROWS = 262144;   // 2^18: with BETA = 53, 2^18 * 2^106 < P/2
+constexpr int64_t UNIT_ROWS_MAX = 65536;
+constexpr int CV_ROWS = 128, CV_COLS = 32, CV_THREADS = 256;
+
+struct I8Tables {
+  int mod[NMOD];
+  int half[NMOD];
+  unsigned magic[NMOD];     // floor(2^32 / p) + 1: exact floor(u / p) for u < 2^23
+  int off[NMOD];            // p * 2048 + half: makes the dp4a sum positive, folds the symmetric shift
+  int wlo[NMOD], whi[NMOD]; // packed int8 weights 256^i mod p (i = 0..3 | 4..6, sign weight -2^56 mod p)
+  int garner_w[NMOD][NMOD]; // (p_0 ... p_{j-1}) mod p_k
+  int garner_inv[NMOD];     // (p_0 ... p_{k-1})^-1 mod p_k
+  unsigned long long p_lo, p_hi;        // P = prod p_t
+  unsigned long long half_lo, half_hi;  // floor(P / 2)
+};
+
+constexpr int kMods[NMOD] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193};
+
+constexpr int sym_mod(long long x, int p) {
+  long long r = x % p;
+  if (r < 0) r += p;
+  return (int)(r > p / 2 ? r - p : r);
+}
+constexpr int pow_mod(int base, int e, int p) {
+  long long r = 1, b = base % p;
+  for (int i = 0; i < e; ++i) r = (r * b) % p;
+  return (int)r;
+}
+constexpr int inv_mod(int a, int p) {
+  a %= p;
+  for (int x = 1; x < p; ++x)
+    if ((a * x) % p == 1) return x;
+  return 0;
+}
+constexpr int pack4(int a, int b, int c, int d) {
+  return (int)(((unsigned)(a & 255)) | ((unsigned)(b & 255) << 8) | ((unsigned)(c & 255) << 16) |
+               ((unsigned)(d & 255) << 24));
+}
+constexpr I8Tables make_tables() {
+  I8Tables t{};
+  unsigned __int128 P = 1;
+  for (int i = 0; i < NMOD; ++i) {
+    const int p = kMods[i];
+    t.mod[i] = p;
+    t.half[i] = p / 2;
+    t.magic[i] = (unsigned)((1ull << 32) / (unsigned)p + 1ull);
+    t.off[i] = p * 2048 + p / 2;
+    int w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < 7; ++j) w[j] = sym_mod(pow_mod(256, j, p), p);
+    w[7] = sym_mod(-(long long)pow_mod(256, 7, p), p);
+    t.wlo[i] = pack4(w[0], w[1], w[2], w[3]);
+    t.whi[i] = pack4(w[4], w[5], w[6], w[7]);
+    int prod = 1;
+    for (int j = 0; j < NMOD; ++j) {
+      t.garner_w[i][j] = j < i ? prod : 0;
+      if (j < i) prod = (prod * (kMods[j] % p)) % p;
+    }
+    t.garner_inv[i] = i == 0 ? 1 : inv_mod(prod, p);
+    P *= (unsigned)p;
+  }
+  t.p_lo = (unsigned long long)P;
+  t.p_hi = (unsigned long long)(P >> 64);
+  const unsigned __int128 H = P >> 1;
+  t.half_lo = (unsigned long long)H;
+  t.half_hi = (unsigned long long)(H >> 64);
+  return t;
+}
+
+__constant__ I8Tables c_tab = make_tables();
+
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded spin: a protocol error becomes a launch failure (trap) instead of a hung GPU
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  for (unsigned spin = 0; spin < (1u << 22); ++spin) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                          unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(unsigned taddr, unsigned (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 bytes apart
+__device__ __forceinline__ unsigned long long umma_desc_sw128(unsigned smem_addr) {
+  unsigned long long d = 0;
+  d |= (unsigned long long)((smem_addr & 0x3FFFFu) >> 4);   // start address
+  d |= (unsigned long long)(1024u >> 4) << 32;              // stride byte offset (between 8-row groups)
+  d |= 1ull << 46;                                          // descriptor version (sm_100)
+  d |= 2ull << 61;                                          // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor of kind::i8: D = s32, A = B = signed 8 bit, both K-major, dense
+__device__ __forceinline__ unsigned umma_idesc_i8(int m, int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ 1
+// column maxima of |w a| over the slab; bit patterns of non-negative doubles order like integers
+__global__ void __launch_bounds__(256) i8_colmax_kernel(const double* __restrict__ A, int64_t lda,
+                                                        const double* __restrict__ b,
+                                                        const double* __restrict__ weff, int64_t nrows, int k,
+                                                        int64_t rows_per_cta, unsigned long long* __restrict__ colmax,
+                                                        int* __restrict__ nonfinite) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int ka = k + 1;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+  int64_t r1 = r0 + rows_per_cta;
+  if (r1 > nrows) r1 = nrows;
+  if (c >= ka) return;
+  const double* src = (c < k) ? A + c : b;
+  const int64_t stride = (c < k) ? lda : 1;
+  double m = 0.0;
+  bool bad = false;
+  int64_t r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    double v[8], wv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      v[q] = __ldg(src + (r + q) * stride);
+      wv[q] = __ldg(weff + r + q);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const double t = fabs(v[q] * wv[q]);
+      bad |= !(t <= 1.7976931348623157e308);
+      m = fmax(m, t);
+    }
+  }
+  for (; r < r1; ++r) {
+    const double t = fabs(__ldg(src + r * stride) * __ldg(weff + r));
+    bad |= !(t <= 1.7976931348623157e308);
+    m = fmax(m, t);
+  }
+  if (bad) atomicAdd(nonfinite, 1);
+  if (m > 0.0 && !bad) atomicMax(colmax + c, (unsigned long long)__double_as_longlong(m));
+}
+
+__device__ __forceinline__ int scale_exponent(unsigned long long max_bits, int beta) {
+  const double m = __longlong_as_double((long long)max_bits);
+  if (!(m > 0.0)) return 0;
+  int e = beta - 1 - ilogb(m);
+  if (e > 1000) e = 1000;
+  if (e < -1000) e = -1000;
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------------ 2
+// residue planes: planes[(t * kpc + c) * ldr + r] = (rint(w_r a_rc 2^e_c)) mod p_t, symmetric, int8
+__global__ void __launch_bounds__(CV_THREADS) i8_convert_kernel(const double* __restrict__ A, int64_t lda,
+                                                               const double* __restrict__ b,
+                                                               const double* __restrict__ weff, int64_t nrows,
+                                                               int k, const unsigned long long* __restrict__ colmax,
+                                                               int beta, unsigned* __restrict__ planes, int64_t ldr,
+                                                               int kpc, int n_rowtiles) {
+  extern __shared__ unsigned cv_sm[];   // [NMOD][32 columns][33]: word g of a column = residues of rows 4g..4g+3
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ka = k + 1;
+  const int n_coltiles = kpc / CV_COLS;
+  const int64_t ntiles = (int64_t)n_rowtiles * n_coltiles;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int ct = (int)(tile % n_coltiles);
+    const int64_t rt = tile / n_coltiles;
+    const int c = ct * CV_COLS + lane;
+    double scale = 0.0;
+    if (c < ka)   // 2^e, e in [-1000, 1000]: assemble the exponent field directly
+      scale = __longlong_as_double((long long)(scale_exponent(colmax[c], beta) + 1023) << 52);
+    const double* src = (c < k) ? A + c : b;
+    const int64_t stride = (c < k) ? lda : 1;
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) {
+      const int g = warp * 4 + gi;
+      const int64_t rbase = rt * CV_ROWS + g * 4;
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t r = rbase + q;
+        v[q] = 0.0;
+        if (r < nrows && c < ka) v[q] = __ldg(src + r * stride) * __ldg(weff + r);   // fl(w*a), svd.py:44
+      }
+      unsigned lo[4], hi[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long iv = __double2ll_rn(v[q] * scale);
+        lo[q] = (unsigned)iv;
+        hi[q] = ((unsigned)((unsigned long long)iv >> 32) & 0x00FFFFFFu) | (iv < 0 ? 0x01000000u : 0u);
+      }
+#pragma unroll
+      for (int t = 0; t < NMOD; ++t) {
+        int res[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const unsigned u = (unsigned)dp4a_us(hi[q], c_tab.whi[t], dp4a_us(lo[q], c_tab.wlo[t], c_tab.off[t]));
+          const unsigned qq = __umulhi(u, c_tab.magic[t]);
+          res[q] = (int)(u - qq * (unsigned)c_tab.mod[t]) - c_tab.half[t];
+        }
+        const unsigned t01 = __byte_perm((unsigned)res[0], (unsigned)res[1], 0x0040);
+        const unsigned t23 = __byte_perm((unsigned)res[2], (unsigned)res[3], 0x0040);
+        cv_sm[(t * CV_COLS + lane) * 33 + g] = __byte_perm(t01, t23, 0x5410);
+      }
+    }
+    __syncthreads();
+    // 16 x 32 lines of 128 bytes: line (t, cc) holds the 128 rows of column cc in plane t
+    for (int line = warp; line < NMOD * CV_COLS; line += CV_THREADS / 32) {
+      const int t = line >> 5, cc = line & 31;
+      const unsigned word = cv_sm[(t * CV_COLS + cc) * 33 + lane];
+      planes[(((size_t)t * kpc + ct * CV_COLS + cc) * (size_t)ldr + (size_t)rt * CV_ROWS) / 4 + lane] = word;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 3
+struct GemmArgs {
+  int n_i;                 // 128-column blocks of the augmented matrix
+  int ntile;               // (I, JJ) tiles of the lower triangle
+  int ka;
+  int kp;                  // leading dimension of the int64 table (n_i * 128)
+  int64_t slab_rows;
+  int64_t unit_rows;
+  long long* table;        // [NMOD][kp (column j)][kp (row i)]
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) i8_gemm_kernel(const __grid_constant__ CUtensorMap tmap, GemmArgs p) {
+  extern __shared__ __align__(1024) unsigned char gm_sm[];
+  __shared__ __align__(8) unsigned long long s_full[NST];
+  __shared__ __align__(8) unsigned long long s_empty[NST];
+  __shared__ __align__(8) unsigned long long s_acc;
+  __shared__ unsigned s_tmem;
+
+  // 1024-byte aligned stage buffers (128-byte swizzle atoms are 1024 bytes)
+  const unsigned sm_base = (smem_u32(gm_sm) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // work unit: tile fastest (the tiles of one (chunk, modulus) run together and share the plane rows in L2)
+  int unit = blockIdx.x;
+  const int tile = unit % p.ntile;
+  unit /= p.ntile;
+  const int t = unit % NMOD;
+  const int64_t chunk = unit / NMOD;
+  int ti = 0, tj = 0;
+  {
+    int rem = tile;
+    for (ti = 0; ti < p.n_i; ++ti) {
+      const int cnt = ti / 2 + 1;
+      if (rem < cnt) { tj = rem; break; }
+      rem -= cnt;
+    }
+  }
+  const int col_i = ti * BM, col_j = tj * BN;
+  const bool wide = (col_j + BM) < p.n_i * BM;   // second 128-column half of JJ exists
+  const int n_mma = wide ? BN : BM;
+  const int64_t row0 = chunk * p.unit_rows;
+  int64_t row1 = row0 + p.unit_rows;
+  if (row1 > p.slab_rows) row1 = p.slab_rows;
+  const int nks = (int)((row1 - row0 + BK - 1) / BK);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&s_empty[i]), 1);
+    }
+    mbar_init(smem_u32(&s_acc), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                 "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem = s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const unsigned bytes = (unsigned)(A_BYTES + n_mma * BK);
+      for (int ks = 0; ks < nks; ++ks) {
+        const int slot = ks % NST, n = ks / NST;
+        if (ks >= NST) mbar_wait(smem_u32(&s_empty[slot]), (unsigned)((n - 1) & 1));
+        const unsigned full = smem_u32(&s_full[slot]);
+        const unsigned dst = sm_base + (unsigned)slot * STAGE_BYTES;
+        const int r = (int)(row0 + (int64_t)ks * BK);
+        mbar_expect_tx(full, bytes);
+        tma_load_3d(dst, &tmap, r, col_i, t, full);
+        tma_load_3d(dst + A_BYTES, &tmap, r, col_j, t, full);
+        if (wide) tma_load_3d(dst + A_BYTES + BM * BK, &tmap, r, col_j + BM, t, full);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const unsigned idesc = umma_idesc_i8(BM, n_mma);
+      for (int ks = 0; ks < nks; ++ks) {
+        const int slot = ks % NST, n = ks / NST;
+        mbar_wait(smem_u32(&s_full[slot]), (unsigned)(n & 1));
+        tc_fence_after();
+        const unsigned a_addr = sm_base + (unsigned)slot * STAGE_BYTES;
+        const unsigned long long adesc = umma_desc_sw128(a_addr);
+        const unsigned long long bdesc = umma_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+        for (int k4 = 0; k4 < BK / UK; ++k4)   // +32 bytes of K inside the swizzle atom = +2 in the address field
+          tc_mma_i8(tmem, adesc + (unsigned long long)(2 * k4), bdesc + (unsigned long long)(2 * k4), idesc,
+                    (unsigned)((ks | k4) != 0));
+        tc_commit(smem_u32(&s_empty[slot]));   // frees the stage when these MMAs have read it
+      }
+      tc_commit(smem_u32(&s_acc));             // accumulator complete
+    }
+  } else {
+    // epilogue: warp w may touch TMEM lanes [32 (w % 4), +32)
+    const int quad = warp & 3;
+    const int grow = col_i + quad * 32 + lane;   // row i of the Gram (column index of A)
+    mbar_wait(smem_u32(&s_acc), 0);
+    tc_fence_after();
+    long long* tab = p.table + (size_t)t * p.kp * p.kp;
+    for (int c0 = 0; c0 < n_mma; c0 += 32) {
+      if (col_j + c0 > col_i + BM - 1) break;    // the rest of the tile lies above the diagonal
+      unsigned v[32];
+      tc_ld32(tmem + ((unsigned)(quad * 32) << 16) + (unsigned)c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int gcol = col_j + c0 + j;
+        if (grow < p.ka && gcol <= grow && nks > 0)
+          atomicAdd(reinterpret_cast<unsigned long long*>(tab + (size_t)gcol * p.kp + grow),
+                    (unsigned long long)(long long)(int)v[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 4
+// exact reconstruction of the slab's integer Gram and accumulation into gaug (lower triangle + mirror)
+__global__ void __launch_bounds__(128) i8_crt_kernel(long long* __restrict__ table, int kp, int ka,
+                                                     const unsigned long long* __restrict__ colmax, int beta,
+                                                     const int* __restrict__ nonfinite, int first,
+                                                     double* __restrict__ gaug) {
+  const int j = blockIdx.y;
+  const int i = j + blockIdx.x * 128 + threadIdx.x;
+  if (i >= ka) return;
+  int res[NMOD];
+#pragma unroll
+  for (int t = 0; t < NMOD; ++t) {
+    long long* cell = table + ((size_t)t * kp + j) * kp + i;
+    const long long v = *cell;
+    *cell = 0;                                   // ready for the next slab
+    const int p = c_tab.mod[t];
+    int r = (int)(v % p);
+    res[t] = r < 0 ? r + p : r;
+  }
+  // Garner: x = d_0 + d_1 p_0 + d_2 p_0 p_1 + ...
+  int dig[NMOD];
+  dig[0] = res[0];
+#pragma unroll
+  for (int kk = 1; kk < NMOD; ++kk) {
+    const int p = c_tab.mod[kk];
+    int acc = 0;
+#pragma unroll
+    for (int jj = 0; jj < kk; ++jj) acc += dig[jj] * c_tab.garner_w[kk][jj];
+    int d = (res[kk] - acc % p) % p;
+    if (d < 0) d += p;
+    dig[kk] = (d * c_tab.garner_inv[kk]) % p;
+  }
+  unsigned __int128 x = (unsigned)dig[NMOD - 1];
+#pragma unroll
+  for (int kk = NMOD - 2; kk >= 0; --kk) x = x * (unsigned)c_tab.mod[kk] + (unsigned)dig[kk];
+  const unsigned __int128 P = ((unsigned __int128)c_tab.p_hi << 64) | c_tab.p_lo;
+  const unsigned __int128 H = ((unsigned __int128)c_tab.half_hi << 64) | c_tab.half_lo;
+  double sign = 1.0;
+  if (x > H) { x = P - x; sign = -1.0; }
+  // one rounding: normalise to 64 significant bits, keep a sticky bit, let the int64 -> double conversion round
+  const unsigned long long xh = (unsigned long long)(x >> 64), xl = (unsigned long long)x;
+  double val;
+  if (xh == 0) {
+    val = (double)xl;
+  } else {
+    const int sh = 64 - __clzll((long long)xh);            // 1..64 bits live in the high word
+    unsigned long long top = (sh == 64) ? xh : ((xh << (64 - sh)) | (xl >> sh));
+    const unsigned long long lost = (sh == 64) ? xl : (xl << (64 - sh));
+    if (lost) top |= 1ull;
+    val = ldexp((double)top, sh);
+  }
+  const int e = scale_exponent(colmax[i], beta) + scale_exponent(colmax[j], beta);
+  val = sign * ldexp(val, -e);
+  if (*nonfinite) val = __longlong_as_double(0x7ff8000000000000ll);
+  if (first) {
+    gaug[(size_t)i * ka + j] = val;
+    gaug[(size_t)j * ka + i] = val;
+  } else {
+    const double s = gaug[(size_t)i * ka + j] + val;
+    gaug[(size_t)i * ka + j] = s;
+    gaug[(size_t)j * ka + i] = s;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct I8Plan {
+  int ka, n_i, ntile, kp, kpc;
+  int64_t slab_rows, ldr;
+  size_t off_colmax, off_flag, off_table, off_planes, total;
+};
+
+I8Plan plan_i8(int64_t n_rows, int k) {
+  I8Plan pl;
+  pl.ka = k + 1;
+  pl.n_i = (pl.ka + BM - 1) / BM;
+  pl.ntile = 0;
+  for (int i = 0; i < pl.n_i; ++i) pl.ntile += i / 2 + 1;
+  pl.kp = pl.n_i * BM;
+  pl.kpc = (int)fsb_round_up(pl.ka, CV_COLS);
+  const int64_t n = n_rows > 0 ? n_rows : 1;
+  const int64_t nslab = fsb_ceil_div(n, SLAB_ROWS);
+  pl.slab_rows = fsb_round_up(fsb_ceil_div(n, nslab), CV_ROWS);
+  pl.ldr = pl.slab_rows;
+  pl.off_colmax = 0;
+  pl.off_flag = align256((size_t)pl.ka * sizeof(unsigned long long));
+  pl.off_table = pl.off_flag + 256;
+  pl.off_planes = pl.off_table + align256((size_t)NMOD * pl.kp * pl.kp * sizeof(long long));
+  pl.total = pl.off_planes + align256((size_t)NMOD * pl.kpc * (size_t)pl.ldr) + 1024;
+  return pl;
+}
+
+}  // namespace
+
+bool fsb_gram_i8_available() { return get_encode() != nullptr; }
+
+size_t fsb_gram_i8_ws_bytes(int64_t n_rows, int k) { return plan_i8(n_rows, k).total; }
+
+// `weff` already carries the test mask (weight 0); `ws` must be 256-byte aligned and zero-initialised
+// by this function where needed.  gaug is fully overwritten.
+int fsb_launch_gram_i8(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* weff,
+                       int64_t n_rows, int k, double* gaug, void* ws, size_t ws_bytes, cudaStream_t s) {
+  const I8Plan pl = plan_i8(n_rows, k);
+  if (ws_bytes < pl.total) return FSB_ERR_WORKSPACE_TOO_SMALL;
+  if (!get_encode()) return FSB_ERR_UNSUPPORTED;
+  char* base = (char*)ws;
+  unsigned long long* colmax = (unsigned long long*)(base + pl.off_colmax);
+  int* flag = (int*)(base + pl.off_flag);
+  long long* table = (long long*)(base + pl.off_table);
+  char* planes = base + pl.off_planes;
+  planes = (char*)(((uintptr_t)planes + 1023) & ~(uintptr_t)1023);
+  const int ka = pl.ka;
+  const int beta = 53;
+
+  FSB_CUDA_TRY(cudaMemsetAsync(table, 0, (size_t)NMOD * pl.kp * pl.kp * sizeof(long long), s));
+  FSB_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), s));
+  if (n_rows <= 0) {
+    FSB_CUDA_TRY(cudaMemsetAsync(gaug, 0, (size_t)ka * ka * sizeof(double), s));
+    return FSB_OK;
+  }
+  static bool attr_set = false;
+  const size_t gemm_smem = (size_t)NST * STAGE_BYTES + 1024;
+  const size_t cv_smem = (size_t)NMOD * CV_COLS * 33 * sizeof(unsigned);
+  if (!attr_set) {
+    FSB_CUDA_TRY(cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+    FSB_CUDA_TRY(cudaFuncSetAttribute(i8_convert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv_smem));
+    attr_set = true;
+  }
+  int first = 1;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += pl.slab_rows) {
+    const int64_t nr = (n_rows - r0) < pl.slab_rows ? (n_rows - r0) : pl.slab_rows;
+    const double* As = A + r0 * lda;
+    const double* bs = b + r0;
+    const double* ws_ = weff + r0;
+    FSB_CUDA_TRY(cudaMemsetAsync(colmax, 0, (size_t)ka * sizeof(unsigned long long), s));
+    {
+      int64_t rb = fsb_ceil_div(nr, fsb_ceil_div((int64_t)h->sm_count * 8, fsb_ceil_div(ka, 256)));
+      rb = fsb_round_up(rb < 64 ? 64 : rb, 8);
+      dim3 grid((unsigned)fsb_ceil_div(ka, 256), (unsigned)fsb_ceil_div(nr, rb));
+      i8_colmax_kernel<<<grid, 256, 0, s>>>(As, lda, bs, ws_, nr, k, rb, colmax, flag);
+      FSB_LAUNCH_CHECK("i8_colmax_kernel");
+    }
+    const int n_rowtiles = (int)fsb_ceil_div(nr, CV_ROWS);
+    {
+      int64_t ntiles = (int64_t)n_rowtiles * (pl.kpc / CV_COLS);
+      int64_t grid = (int64_t)h->sm_count * 3 * 4;
+      if (grid > ntiles) grid = ntiles;
+      i8_convert_kernel<<<(unsigned)grid, CV_THREADS, cv_smem, s>>>(As, lda, bs, ws_, nr, k, colmax, beta,
+                                                                    (unsigned*)planes, pl.ldr, pl.kpc, n_rowtiles);
+      FSB_LAUNCH_CHECK("i8_convert_kernel");
+    }
+    {
+      CUtensorMap tmap;
+      const cuuint64_t gdim[3] = {(cuuint64_t)nr, (cuuint64_t)pl.kpc, (cuuint64_t)NMOD};
+      const cuuint64_t gstr[2] = {(cuuint64_t)pl.ldr, (cuuint64_t)pl.ldr * (cuuint64_t)pl.kpc};
+      const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      CUresult cr = get_encode()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes, gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) return FSB_ERR_UNSUPPORTED;
+      GemmArgs ga;
+      ga.n_i = pl.n_i; ga.ntile = pl.ntile; ga.ka = ka; ga.kp = pl.kp; ga.slab_rows = nr; ga.table = table;
+      // enough units for ~8 waves, each between 4096 and 65536 rows
+      int64_t want_chunks = fsb_ceil_div((int64_t)h->sm_count * 8, (int64_t)pl.ntile * NMOD);
+      int64_t ur = fsb_round_up(fsb_ceil_div(nr, want_chunks), BK);
+      if (ur < 4096) ur = 4096;
+      if (ur > UNIT_ROWS_MAX) ur = UNIT_ROWS_MAX;
+      ga.unit_rows = ur;
+      const int64_t nchunk = fsb_ceil_div(nr, ur);
+      i8_gemm_kernel<<<(unsigned)(nchunk * NMOD * pl.ntile), GEMM_THREADS, gemm_smem, s>>>(tmap, ga);
+      FSB_LAUNCH_CHECK("i8_gemm_kernel");
+    }
+    {
+      dim3 grid((unsigned)fsb_ceil_div(ka, 128), (unsigned)ka);
+      i8_crt_kernel<<<grid, 128, 0, s>>>(table, pl.kp, ka, colmax, beta, flag, first, gaug);
+      FSB_LAUNCH_CHECK("i8_crt_kernel");
+    }
+    first = 0;
+  }
+  return FSB_OK;
+}

@@ -120,6 +120,16 @@ class Engine:
         lda = A.stride(0) if n > 1 else max(k, A.stride(0))
         return n, k, lda
 
+    def set_gram_path(self, path):
+        """'auto' | 'fp64' (DMMA) | 'int8' (tcgen05 exact-integer Gram); see include/fitsnap_b200.h."""
+        code = {"auto": _cabi.GRAM_AUTO, "fp64": _cabi.GRAM_FP64, "int8": _cabi.GRAM_INT8}[path]
+        _cabi.check("fsb_set_gram_path", self.lib.fsb_set_gram_path(self._h, code))
+
+    def gram_path(self, n_rows, k):
+        out = ctypes.c_int32()
+        _cabi.check("fsb_get_gram_path", self.lib.fsb_get_gram_path(self._h, n_rows, k, ctypes.byref(out)))
+        return {_cabi.GRAM_FP64: "fp64", _cabi.GRAM_INT8: "int8"}[out.value]
+
     # ------------------------------------------------------------------ kernels
     def gram(self, A, b, w, testing=None):
         n, k, lda = self._check_matrix(A, b, w, testing)
@@ -128,8 +138,13 @@ class Engine:
         ws = self._workspace("gram", nbytes)
         _cabi.check("fsb_gram", self.lib.fsb_gram(self._h, _ptr(A), lda, _ptr(b), _ptr(w), _ptr(testing), n, k,
                                                    _ptr(gaug), _ptr(ws), ws.numel(), self._stream()))
-        # narrow: row-split kernel + reduce; wide: pre-weight + TMA kernel + reduce
-        self.launch_count += (2 if k + 1 <= 128 else 3) + (1 if (testing is not None and n > 0) else 0)
+        if self.gram_path(n, k) == "int8":
+            # per slab of 2^18 rows: column maxima, residue conversion, tcgen05 GEMM, CRT
+            self.launch_count += 4 * max(1, -(-n // 262144))
+        else:
+            # narrow: row-split kernel + reduce; wide: pre-weight + TMA kernel + reduce
+            self.launch_count += 2 if k + 1 <= 128 else 3
+        self.launch_count += 1 if (testing is not None and n > 0) else 0
         return gaug
 
     def factor(self, gaug, alpha=0.0):

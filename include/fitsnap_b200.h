@@ -113,7 +113,19 @@ int fsb_scatter(fsb_handle_t h, const double* raw, const int64_t* raw_row_off,
  *   gaug     out, (k+1)x(k+1) row-major symmetric:
  *              [ aw^T aw   aw^T bw ]
  *              [ bw^T aw   bw^T bw ]      aw = w[:,None]*A[train], bw = w*b[train]
+ *
+ * Two arithmetic paths produce gaug (fsb_set_gram_path; default FSB_GRAM_AUTO picks by shape):
+ *   FSB_GRAM_FP64  fp64 tensor-core MMA (DMMA), split-K with a fixed reduction order;
+ *   FSB_GRAM_INT8  exact integer Gram on the int8 tcgen05 tensor cores: the weighted rows are
+ *                  quantised per column to 53-bit integers, contracted modulo 16 coprime moduli
+ *                  (int32 accumulators in tensor memory) and rebuilt by the Chinese remainder
+ *                  theorem -- one rounding per entry, independent of summation order.
+ * Call fsb_set_gram_path BEFORE fsb_gram_workspace_bytes: the workspace size depends on it.
  */
+enum { FSB_GRAM_AUTO = 0, FSB_GRAM_FP64 = 1, FSB_GRAM_INT8 = 2 };
+int fsb_set_gram_path(fsb_handle_t h, int32_t path);
+/* the path fsb_gram will take for this shape under the current setting (FSB_GRAM_FP64 or _INT8) */
+int fsb_get_gram_path(fsb_handle_t h, int64_t n_rows, int32_t k, int32_t* path);
 size_t fsb_gram_workspace_bytes(fsb_handle_t h, int64_t n_rows, int32_t k);
 int fsb_gram(fsb_handle_t h, const double* A, int64_t lda, const double* b, const double* w,
              const uint8_t* testing, int64_t n_rows, int32_t k, double* gaug,
