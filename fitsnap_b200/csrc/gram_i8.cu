@@ -30,6 +30,7 @@
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
+#include <utility>
 
 namespace {
 
@@ -54,6 +55,14 @@ struct I8Tables {
   unsigned magic[NMOD];     // floor(2^32 / p) + 1: exact floor(u / p) for u < 2^23
   int off[NMOD];            // p * 2048 + half: makes the dp4a sum positive, folds the symmetric shift
   int wlo[NMOD], whi[NMOD]; // packed int8 weights 256^i mod p (i = 0..3 | 4..6, sign weight -2^56 mod p)
+  // fp32 reduction of the dp4a sum S (|S| < 2^18), moduli <= 253: the dp4a accumulator starts at the BIT PATTERN
+  // of the float T + 2048 p with T = 2^23 + 256 j = p s (j = -2^15 mod p), so its result, read as a float, is
+  // uf = T + 2048 p + S exactly.  qm = fma(uf, 1/p, 1.5 2^23) rounds uf/p to an integer, q = qm - (1.5 2^23 + s)
+  // = 2048 + rint(S/p), and fma(-q, p, uf) = 2^23 + 256 j + (S - p rint(S/p)): its low byte is the symmetric
+  // residue in two's complement.  Three fp32 operations, no integer<->float conversion instruction.
+  int finit[NMOD];
+  float fsub[NMOD], finv[NMOD], fmod[NMOD];
+  double dinv[NMOD];
   int garner_w[NMOD][NMOD]; // (p_0 ... p_{j-1}) mod p_k
   int garner_inv[NMOD];     // (p_0 ... p_{k-1})^-1 mod p_k
   unsigned long long p_lo, p_hi;        // P = prod p_t
@@ -96,6 +105,16 @@ constexpr I8Tables make_tables() {
     w[7] = sym_mod(-(long long)pow_mod(256, 7, p), p);
     t.wlo[i] = pack4(w[0], w[1], w[2], w[3]);
     t.whi[i] = pack4(w[4], w[5], w[6], w[7]);
+    {
+      int j = (int)((((-32768ll) % p) + p) % p);
+      if (j == 0) j = p;
+      const int T = (1 << 23) + 256 * j;          // multiple of p (p odd)
+      t.finit[i] = 0x4B000000 + 256 * j + 2048 * p;
+      t.fsub[i] = (float)(12582912 + (p % 2 ? T / p : 0));
+      t.finv[i] = 1.0f / (float)p;
+      t.fmod[i] = (float)p;
+      t.dinv[i] = 1.0 / (double)p;
+    }
     int prod = 1;
     for (int j = 0; j < NMOD; ++j) {
       t.garner_w[i][j] = j < i ? prod : 0;
@@ -242,68 +261,85 @@ __device__ __forceinline__ int scale_exponent(unsigned long long max_bits, int b
   return e;
 }
 
+// residues of four rows (one column) modulo p_T, packed into one word of the staging tile
+template <int T>
+__device__ __forceinline__ void convert_one_modulus(const unsigned (&lo)[4], const unsigned (&hi)[4], unsigned* dst) {
+  constexpr int P = kMods[T];
+  unsigned res[4];   // residue of row q in the low byte
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if constexpr (P == 256) {          // two's complement low byte
+      res[q] = lo[q];
+    } else if constexpr (P > 253) {    // 255: no slack for a sloppy quotient, exact integer reduction
+      const unsigned u = (unsigned)dp4a_us(hi[q], c_tab.whi[T], dp4a_us(lo[q], c_tab.wlo[T], c_tab.off[T]));
+      const unsigned qq = __umulhi(u, c_tab.magic[T]);
+      res[q] = (unsigned)((int)(u - qq * (unsigned)P) - P / 2);
+    } else {
+      const float uf = __int_as_float(dp4a_us(hi[q], c_tab.whi[T], dp4a_us(lo[q], c_tab.wlo[T], c_tab.finit[T])));
+      const float qm = __fmaf_rn(uf, c_tab.finv[T], 12582912.0f);
+      const float qq = __fsub_rn(qm, c_tab.fsub[T]);
+      res[q] = (unsigned)__float_as_int(__fmaf_rn(-qq, (float)P, uf));
+    }
+  }
+  const unsigned t01 = __byte_perm(res[0], res[1], 0x0040);
+  const unsigned t23 = __byte_perm(res[2], res[3], 0x0040);
+  dst[T * CV_COLS * 33] = __byte_perm(t01, t23, 0x5410);
+}
+template <int... T>
+__device__ __forceinline__ void convert_all_moduli(const unsigned (&lo)[4], const unsigned (&hi)[4], unsigned* dst,
+                                                   std::integer_sequence<int, T...>) {
+  (convert_one_modulus<T>(lo, hi, dst), ...);
+}
+
 // ------------------------------------------------------------------------------------------------ 2
 // residue planes: planes[(t * kpc + c) * ldr + r] = (rint(w_r a_rc 2^e_c)) mod p_t, symmetric, int8
-__global__ void __launch_bounds__(CV_THREADS) i8_convert_kernel(const double* __restrict__ A, int64_t lda,
-                                                               const double* __restrict__ b,
-                                                               const double* __restrict__ weff, int64_t nrows,
-                                                               int k, const unsigned long long* __restrict__ colmax,
-                                                               int beta, unsigned* __restrict__ planes, int64_t ldr,
-                                                               int kpc, int n_rowtiles) {
+__global__ void __launch_bounds__(CV_THREADS, 3) i8_convert_kernel(const double* __restrict__ A, int64_t lda,
+                                                                  const double* __restrict__ b,
+                                                                  const double* __restrict__ weff, int64_t nrows,
+                                                                  int k, const unsigned long long* __restrict__ colmax,
+                                                                  int beta, unsigned* __restrict__ planes, int64_t ldr,
+                                                                  int kpc) {
   extern __shared__ unsigned cv_sm[];   // [NMOD][32 columns][33]: word g of a column = residues of rows 4g..4g+3
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ka = k + 1;
-  const int n_coltiles = kpc / CV_COLS;
-  const int64_t ntiles = (int64_t)n_rowtiles * n_coltiles;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int ct = (int)(tile % n_coltiles);
-    const int64_t rt = tile / n_coltiles;
-    const int c = ct * CV_COLS + lane;
-    double scale = 0.0;
-    if (c < ka)   // 2^e, e in [-1000, 1000]: assemble the exponent field directly
-      scale = __longlong_as_double((long long)(scale_exponent(colmax[c], beta) + 1023) << 52);
-    const double* src = (c < k) ? A + c : b;
-    const int64_t stride = (c < k) ? lda : 1;
+  const int ct = blockIdx.x;            // one CTA = one tile of 128 rows x 32 columns (short-lived on purpose:
+  const int64_t rt = blockIdx.y;        // the tensor-core kernel of the previous slab shares the SMs)
+  const int c = ct * CV_COLS + lane;
+  double scale = 0.0;
+  if (c < ka)   // 2^e, e in [-1000, 1000]: assemble the exponent field directly
+    scale = __longlong_as_double((long long)(scale_exponent(colmax[c], beta) + 1023) << 52);
+  const double* src = (c < k) ? A + c : b;
+  const int64_t stride = (c < k) ? lda : 1;
+  // all 16 loads of this thread are issued before the first use (rows past the end: clamped address, weight 0)
+  double v[16], wv[16];
+  const int64_t rbase = rt * CV_ROWS + warp * 16;
 #pragma unroll
-    for (int gi = 0; gi < 4; ++gi) {
-      const int g = warp * 4 + gi;
-      const int64_t rbase = rt * CV_ROWS + g * 4;
-      double v[4];
+  for (int q = 0; q < 16; ++q) {
+    const int64_t r = rbase + q;
+    const int64_t rc = r < nrows ? r : nrows - 1;
+    v[q] = __ldg(src + rc * stride);
+    wv[q] = r < nrows ? __ldg(weff + rc) : 0.0;
+  }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int64_t r = rbase + q;
-        v[q] = 0.0;
-        if (r < nrows && c < ka) v[q] = __ldg(src + r * stride) * __ldg(weff + r);   // fl(w*a), svd.py:44
-      }
-      unsigned lo[4], hi[4];
+  for (int q = 0; q < 16; ++q) v[q] *= wv[q];   // fl(w*a): the reference's aw (svd.py:44)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const long long iv = __double2ll_rn(v[q] * scale);
-        lo[q] = (unsigned)iv;
-        hi[q] = ((unsigned)((unsigned long long)iv >> 32) & 0x00FFFFFFu) | (iv < 0 ? 0x01000000u : 0u);
-      }
+  for (int gi = 0; gi < 4; ++gi) {
+    unsigned lo[4], hi[4];
 #pragma unroll
-      for (int t = 0; t < NMOD; ++t) {
-        int res[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const unsigned u = (unsigned)dp4a_us(hi[q], c_tab.whi[t], dp4a_us(lo[q], c_tab.wlo[t], c_tab.off[t]));
-          const unsigned qq = __umulhi(u, c_tab.magic[t]);
-          res[q] = (int)(u - qq * (unsigned)c_tab.mod[t]) - c_tab.half[t];
-        }
-        const unsigned t01 = __byte_perm((unsigned)res[0], (unsigned)res[1], 0x0040);
-        const unsigned t23 = __byte_perm((unsigned)res[2], (unsigned)res[3], 0x0040);
-        cv_sm[(t * CV_COLS + lane) * 33 + g] = __byte_perm(t01, t23, 0x5410);
-      }
+    for (int q = 0; q < 4; ++q) {
+      const long long iv = __double2ll_rn(v[gi * 4 + q] * scale);
+      lo[q] = (unsigned)iv;
+      hi[q] = ((unsigned)((unsigned long long)iv >> 32) & 0x00FFFFFFu) | (iv < 0 ? 0x01000000u : 0u);
     }
-    __syncthreads();
-    // 16 x 32 lines of 128 bytes: line (t, cc) holds the 128 rows of column cc in plane t
-    for (int line = warp; line < NMOD * CV_COLS; line += CV_THREADS / 32) {
-      const int t = line >> 5, cc = line & 31;
-      const unsigned word = cv_sm[(t * CV_COLS + cc) * 33 + lane];
-      planes[(((size_t)t * kpc + ct * CV_COLS + cc) * (size_t)ldr + (size_t)rt * CV_ROWS) / 4 + lane] = word;
-    }
-    __syncthreads();
+    convert_all_moduli(lo, hi, cv_sm + lane * 33 + warp * 4 + gi, std::make_integer_sequence<int, NMOD>{});
+  }
+  __syncthreads();
+  // 16 x 32 lines of 128 bytes: line (t, cc) holds the 128 rows of column cc in plane t
+#pragma unroll 8
+  for (int line = warp; line < NMOD * CV_COLS; line += CV_THREADS / 32) {
+    const int t = line >> 5, cc = line & 31;
+    const unsigned word = cv_sm[(t * CV_COLS + cc) * 33 + lane];
+    planes[(((size_t)t * kpc + ct * CV_COLS + cc) * (size_t)ldr + (size_t)rt * CV_ROWS) / 4 + lane] = word;
   }
 }
 
@@ -447,22 +483,27 @@ __global__ void __launch_bounds__(128) i8_crt_kernel(long long* __restrict__ tab
     long long* cell = table + ((size_t)t * kp + j) * kp + i;
     const long long v = *cell;
     *cell = 0;                                   // ready for the next slab
+    // |v| <= 4 units x 2^30: quotient estimate in fp64, then one correction step either way
     const int p = c_tab.mod[t];
-    int r = (int)(v % p);
-    res[t] = r < 0 ? r + p : r;
+    int r = (int)(v - (long long)floor((double)v * c_tab.dinv[t]) * p);
+    r = r < 0 ? r + p : r;
+    r = r >= p ? r - p : r;
+    res[t] = r;
   }
-  // Garner: x = d_0 + d_1 p_0 + d_2 p_0 p_1 + ...
+  // Garner: x = d_0 + d_1 p_0 + d_2 p_0 p_1 + ...   (all operands < 2^21: floor(u/p) = umulhi(u, magic))
   int dig[NMOD];
   dig[0] = res[0];
 #pragma unroll
   for (int kk = 1; kk < NMOD; ++kk) {
-    const int p = c_tab.mod[kk];
-    int acc = 0;
+    const unsigned p = (unsigned)c_tab.mod[kk];
+    unsigned acc = 0;
 #pragma unroll
-    for (int jj = 0; jj < kk; ++jj) acc += dig[jj] * c_tab.garner_w[kk][jj];
-    int d = (res[kk] - acc % p) % p;
-    if (d < 0) d += p;
-    dig[kk] = (d * c_tab.garner_inv[kk]) % p;
+    for (int jj = 0; jj < kk; ++jj) acc += (unsigned)(dig[jj] * c_tab.garner_w[kk][jj]);
+    acc -= __umulhi(acc, c_tab.magic[kk]) * p;                 // acc mod p
+    unsigned d = (unsigned)res[kk] + p - acc;                  // in (0, 2p)
+    d = d >= p ? d - p : d;
+    d *= (unsigned)c_tab.garner_inv[kk];
+    dig[kk] = (int)(d - __umulhi(d, c_tab.magic[kk]) * p);
   }
   unsigned __int128 x = (unsigned)dig[NMOD - 1];
 #pragma unroll
@@ -592,13 +633,10 @@ int fsb_launch_gram_i8(const fsb_context* h, const double* A, int64_t lda, const
       i8_colmax_kernel<<<grid, 256, 0, s>>>(As, lda, bs, ws_, nr, k, rb, colmax, flag);
       FSB_LAUNCH_CHECK("i8_colmax_kernel");
     }
-    const int n_rowtiles = (int)fsb_ceil_div(nr, CV_ROWS);
     {
-      int64_t ntiles = (int64_t)n_rowtiles * (pl.kpc / CV_COLS);
-      int64_t grid = (int64_t)h->sm_count * 3 * 4;
-      if (grid > ntiles) grid = ntiles;
-      i8_convert_kernel<<<(unsigned)grid, CV_THREADS, cv_smem, s>>>(As, lda, bs, ws_, nr, k, colmax, beta,
-                                                                    (unsigned*)planes, pl.ldr, pl.kpc, n_rowtiles);
+      dim3 grid((unsigned)(pl.kpc / CV_COLS), (unsigned)fsb_ceil_div(nr, CV_ROWS));
+      i8_convert_kernel<<<grid, CV_THREADS, cv_smem, s>>>(As, lda, bs, ws_, nr, k, colmax, beta, (unsigned*)planes,
+                                                          pl.ldr, pl.kpc);
       FSB_LAUNCH_CHECK("i8_convert_kernel");
     }
     {
