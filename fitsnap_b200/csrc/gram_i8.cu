@@ -44,7 +44,7 @@ constexpr int A_BYTES = BM * BK;        // 16 KB
 constexpr int B_BYTES = BN * BK;        // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_THREADS = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 512;       // two 128 x 256 int32 accumulators
 constexpr int64_t SLAB_ROWS = 262144;   // 2^18: with BETA = 53, 2^18 * 2^106 < P/2
 constexpr int64_t UNIT_ROWS_MAX = 65536;
 constexpr int CV_ROWS = 128, CV_COLS = 32, CV_THREADS = 256;
@@ -261,9 +261,10 @@ __device__ __forceinline__ int scale_exponent(unsigned long long max_bits, int b
   return e;
 }
 
-// residues of four rows (one column) modulo p_T, packed into one word of the staging tile
+// residues of four consecutive rows (one column) modulo p_T, packed into one word of plane T
 template <int T>
-__device__ __forceinline__ void convert_one_modulus(const unsigned (&lo)[4], const unsigned (&hi)[4], unsigned* dst) {
+__device__ __forceinline__ void convert_one_modulus(const unsigned (&lo)[4], const unsigned (&hi)[4], unsigned* dst,
+                                                    size_t plane_words) {
   constexpr int P = kMods[T];
   unsigned res[4];   // residue of row q in the low byte
 #pragma unroll
@@ -283,63 +284,69 @@ __device__ __forceinline__ void convert_one_modulus(const unsigned (&lo)[4], con
   }
   const unsigned t01 = __byte_perm(res[0], res[1], 0x0040);
   const unsigned t23 = __byte_perm(res[2], res[3], 0x0040);
-  dst[T * CV_COLS * 33] = __byte_perm(t01, t23, 0x5410);
+  dst[(size_t)T * plane_words] = __byte_perm(t01, t23, 0x5410);
 }
 template <int... T>
 __device__ __forceinline__ void convert_all_moduli(const unsigned (&lo)[4], const unsigned (&hi)[4], unsigned* dst,
-                                                   std::integer_sequence<int, T...>) {
-  (convert_one_modulus<T>(lo, hi, dst), ...);
+                                                   size_t plane_words, std::integer_sequence<int, T...>) {
+  (convert_one_modulus<T>(lo, hi, dst, plane_words), ...);
 }
 
 // ------------------------------------------------------------------------------------------------ 2
 // residue planes: planes[(t * kpc + c) * ldr + r] = (rint(w_r a_rc 2^e_c)) mod p_t, symmetric, int8
+// A warp owns 4 columns x 128 rows: lane l holds rows 4l..4l+3 of each, so every store instruction writes one
+// full 128-byte line of one plane (no shared-memory transpose) and every load fetches whole 32-byte sectors.
 __global__ void __launch_bounds__(CV_THREADS, 3) i8_convert_kernel(const double* __restrict__ A, int64_t lda,
                                                                   const double* __restrict__ b,
                                                                   const double* __restrict__ weff, int64_t nrows,
                                                                   int k, const unsigned long long* __restrict__ colmax,
                                                                   int beta, unsigned* __restrict__ planes, int64_t ldr,
                                                                   int kpc) {
-  extern __shared__ unsigned cv_sm[];   // [NMOD][32 columns][33]: word g of a column = residues of rows 4g..4g+3
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ka = k + 1;
-  const int ct = blockIdx.x;            // one CTA = one tile of 128 rows x 32 columns (short-lived on purpose:
-  const int64_t rt = blockIdx.y;        // the tensor-core kernel of the previous slab shares the SMs)
-  const int c = ct * CV_COLS + lane;
-  double scale = 0.0;
-  if (c < ka)   // 2^e, e in [-1000, 1000]: assemble the exponent field directly
-    scale = __longlong_as_double((long long)(scale_exponent(colmax[c], beta) + 1023) << 52);
-  const double* src = (c < k) ? A + c : b;
-  const int64_t stride = (c < k) ? lda : 1;
-  // all 16 loads of this thread are issued before the first use (rows past the end: clamped address, weight 0)
-  double v[16], wv[16];
-  const int64_t rbase = rt * CV_ROWS + warp * 16;
-#pragma unroll
-  for (int q = 0; q < 16; ++q) {
-    const int64_t r = rbase + q;
-    const int64_t rc = r < nrows ? r : nrows - 1;
-    v[q] = __ldg(src + rc * stride);
-    wv[q] = r < nrows ? __ldg(weff + rc) : 0.0;
+  const int c0 = blockIdx.x * CV_COLS + warp * 4;       // first of this warp's 4 columns
+  const int64_t r0 = (int64_t)blockIdx.y * CV_ROWS + lane * 4;
+  if (c0 >= ka) {                                        // padding columns of the last tile: zero residues
+    for (int j = 0; j < 4; ++j)
+      for (int t = 0; t < NMOD; ++t) planes[(((size_t)t * kpc + c0 + j) * (size_t)ldr + r0) / 4] = 0u;
+    return;
   }
+  double v[4][4], wv[4];
+  const bool vec = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
 #pragma unroll
-  for (int q = 0; q < 16; ++q) v[q] *= wv[q];   // fl(w*a): the reference's aw (svd.py:44)
+  for (int q = 0; q < 4; ++q) {
+    const int64_t r = r0 + q;
+    const int64_t rc = r < nrows ? r : nrows - 1;         // rows past the end: clamped address, weight 0
+    wv[q] = r < nrows ? __ldg(weff + rc) : 0.0;
+    const double* row = A + rc * lda;
+    if (vec && c0 + 3 < k) {     // whole 32-byte sector of this row in two 16-byte loads
+      const double2 x0 = __ldg(reinterpret_cast<const double2*>(row + c0));
+      const double2 x1 = __ldg(reinterpret_cast<const double2*>(row + c0 + 2));
+      v[q][0] = x0.x; v[q][1] = x0.y; v[q][2] = x1.x; v[q][3] = x1.y;
+    } else {
 #pragma unroll
-  for (int gi = 0; gi < 4; ++gi) {
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j;
+        v[q][j] = (c < k) ? __ldg(row + c) : ((c == k) ? __ldg(b + rc) : 0.0);
+      }
+    }
+  }
+  const size_t plane_words = (size_t)kpc * (size_t)ldr / 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + j;
+    double scale = 0.0;
+    if (c < ka)   // 2^e, e in [-1000, 1000]: assemble the exponent field directly
+      scale = __longlong_as_double((long long)(scale_exponent(__ldg(colmax + c), beta) + 1023) << 52);
     unsigned lo[4], hi[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const long long iv = __double2ll_rn(v[gi * 4 + q] * scale);
+      const long long iv = __double2ll_rn((v[q][j] * wv[q]) * scale);   // fl(w*a) first: the reference's aw (svd.py:44)
       lo[q] = (unsigned)iv;
       hi[q] = ((unsigned)((unsigned long long)iv >> 32) & 0x00FFFFFFu) | (iv < 0 ? 0x01000000u : 0u);
     }
-    convert_all_moduli(lo, hi, cv_sm + lane * 33 + warp * 4 + gi, std::make_integer_sequence<int, NMOD>{});
-  }
-  __syncthreads();
-  // 16 x 32 lines of 128 bytes: line (t, cc) holds the 128 rows of column cc in plane t
-#pragma unroll 8
-  for (int line = warp; line < NMOD * CV_COLS; line += CV_THREADS / 32) {
-    const int t = line >> 5, cc = line & 31;
-    const unsigned word = cv_sm[(t * CV_COLS + cc) * 33 + lane];
-    planes[(((size_t)t * kpc + ct * CV_COLS + cc) * (size_t)ldr + (size_t)rt * CV_ROWS) / 4 + lane] = word;
+    convert_all_moduli(lo, hi, planes + ((size_t)c * (size_t)ldr + r0) / 4, plane_words,
+                       std::make_integer_sequence<int, NMOD>{});
   }
 }
 
@@ -349,51 +356,68 @@ struct GemmArgs {
   int ntile;               // (I, JJ) tiles of the lower triangle
   int ka;
   int kp;                  // leading dimension of the int64 table (n_i * 128)
+  int nunits;              // chunks x NMOD x ntile
   int64_t slab_rows;
   int64_t unit_rows;
   long long* table;        // [NMOD][kp (column j)][kp (row i)]
 };
 
+struct Unit {
+  int t, col_i, col_j, n_mma, nks;
+  int64_t row0;
+  bool wide;
+};
+
+// unit index -> (row chunk, modulus, tile); tile fastest: the tiles of one (chunk, modulus) run at the same
+// time on neighbouring SMs and share the plane rows in L2
+__device__ __forceinline__ Unit decode_unit(const GemmArgs& p, int unit) {
+  Unit u;
+  const int tile = unit % p.ntile;
+  unit /= p.ntile;
+  u.t = unit % NMOD;
+  const int64_t chunk = unit / NMOD;
+  int ti = 0, tj = 0, rem = tile;
+  for (ti = 0; ti < p.n_i; ++ti) {
+    const int cnt = ti / 2 + 1;
+    if (rem < cnt) { tj = rem; break; }
+    rem -= cnt;
+  }
+  u.col_i = ti * BM;
+  u.col_j = tj * BN;
+  u.wide = (u.col_j + BM) < p.n_i * BM;   // second 128-column half of JJ exists
+  u.n_mma = u.wide ? BN : BM;
+  u.row0 = chunk * p.unit_rows;
+  int64_t row1 = u.row0 + p.unit_rows;
+  if (row1 > p.slab_rows) row1 = p.slab_rows;
+  u.nks = (int)((row1 - u.row0 + BK - 1) / BK);
+  return u;
+}
+
+// Persistent: one CTA per SM walks units blockIdx.x, blockIdx.x + gridDim.x, ...  (all CTAs of the grid are
+// resident from the start, so the block scheduler can place the conversion kernel of the next slab beside them).
+// Two accumulators in TMEM (2 x 256 columns): the epilogue of unit n drains one while the MMAs of unit n+1
+// fill the other.
 __global__ void __launch_bounds__(GEMM_THREADS, 1) i8_gemm_kernel(const __grid_constant__ CUtensorMap tmap, GemmArgs p) {
   extern __shared__ __align__(1024) unsigned char gm_sm[];
   __shared__ __align__(8) unsigned long long s_full[NST];
   __shared__ __align__(8) unsigned long long s_empty[NST];
-  __shared__ __align__(8) unsigned long long s_acc;
+  __shared__ __align__(8) unsigned long long s_acc_full[2];
+  __shared__ __align__(8) unsigned long long s_acc_empty[2];
   __shared__ unsigned s_tmem;
 
   // 1024-byte aligned stage buffers (128-byte swizzle atoms are 1024 bytes)
   const unsigned sm_base = (smem_u32(gm_sm) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // work unit: tile fastest (the tiles of one (chunk, modulus) run together and share the plane rows in L2)
-  int unit = blockIdx.x;
-  const int tile = unit % p.ntile;
-  unit /= p.ntile;
-  const int t = unit % NMOD;
-  const int64_t chunk = unit / NMOD;
-  int ti = 0, tj = 0;
-  {
-    int rem = tile;
-    for (ti = 0; ti < p.n_i; ++ti) {
-      const int cnt = ti / 2 + 1;
-      if (rem < cnt) { tj = rem; break; }
-      rem -= cnt;
-    }
-  }
-  const int col_i = ti * BM, col_j = tj * BN;
-  const bool wide = (col_j + BM) < p.n_i * BM;   // second 128-column half of JJ exists
-  const int n_mma = wide ? BN : BM;
-  const int64_t row0 = chunk * p.unit_rows;
-  int64_t row1 = row0 + p.unit_rows;
-  if (row1 > p.slab_rows) row1 = p.slab_rows;
-  const int nks = (int)((row1 - row0 + BK - 1) / BK);
-
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) {
       mbar_init(smem_u32(&s_full[i]), 1);
       mbar_init(smem_u32(&s_empty[i]), 1);
     }
-    mbar_init(smem_u32(&s_acc), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s_acc_full[i]), 1);
+      mbar_init(smem_u32(&s_acc_empty[i]), 4);   // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
@@ -409,54 +433,77 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) i8_gemm_kernel(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      const unsigned bytes = (unsigned)(A_BYTES + n_mma * BK);
-      for (int ks = 0; ks < nks; ++ks) {
-        const int slot = ks % NST, n = ks / NST;
-        if (ks >= NST) mbar_wait(smem_u32(&s_empty[slot]), (unsigned)((n - 1) & 1));
-        const unsigned full = smem_u32(&s_full[slot]);
-        const unsigned dst = sm_base + (unsigned)slot * STAGE_BYTES;
-        const int r = (int)(row0 + (int64_t)ks * BK);
-        mbar_expect_tx(full, bytes);
-        tma_load_3d(dst, &tmap, r, col_i, t, full);
-        tma_load_3d(dst + A_BYTES, &tmap, r, col_j, t, full);
-        if (wide) tma_load_3d(dst + A_BYTES + BM * BK, &tmap, r, col_j + BM, t, full);
+      unsigned it = 0;                            // pipeline stage counter, runs on across units
+      for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
+        const Unit u = decode_unit(p, unit);
+        const unsigned bytes = (unsigned)(A_BYTES + u.n_mma * BK);
+        for (int ks = 0; ks < u.nks; ++ks, ++it) {
+          const unsigned slot = it % NST, n = it / NST;
+          if (it >= NST) mbar_wait(smem_u32(&s_empty[slot]), (n - 1) & 1);
+          const unsigned full = smem_u32(&s_full[slot]);
+          const unsigned dst = sm_base + slot * STAGE_BYTES;
+          const int r = (int)(u.row0 + (int64_t)ks * BK);
+          mbar_expect_tx(full, bytes);
+          tma_load_3d(dst, &tmap, r, u.col_i, u.t, full);
+          tma_load_3d(dst + A_BYTES, &tmap, r, u.col_j, u.t, full);
+          if (u.wide) tma_load_3d(dst + A_BYTES + BM * BK, &tmap, r, u.col_j + BM, u.t, full);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const unsigned idesc = umma_idesc_i8(BM, n_mma);
-      for (int ks = 0; ks < nks; ++ks) {
-        const int slot = ks % NST, n = ks / NST;
-        mbar_wait(smem_u32(&s_full[slot]), (unsigned)(n & 1));
+      unsigned it = 0, nu = 0;
+      for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x, ++nu) {
+        const Unit u = decode_unit(p, unit);
+        const unsigned idesc = umma_idesc_i8(BM, u.n_mma);
+        const unsigned ab = nu & 1;               // accumulator buffer
+        if (nu >= 2) mbar_wait(smem_u32(&s_acc_empty[ab]), ((nu >> 1) - 1) & 1);   // drained by the epilogue
         tc_fence_after();
-        const unsigned a_addr = sm_base + (unsigned)slot * STAGE_BYTES;
-        const unsigned long long adesc = umma_desc_sw128(a_addr);
-        const unsigned long long bdesc = umma_desc_sw128(a_addr + A_BYTES);
+        const unsigned acc = tmem + ab * BN;
+        for (int ks = 0; ks < u.nks; ++ks, ++it) {
+          const unsigned slot = it % NST, n = it / NST;
+          mbar_wait(smem_u32(&s_full[slot]), n & 1);
+          tc_fence_after();
+          const unsigned a_addr = sm_base + slot * STAGE_BYTES;
+          const unsigned long long adesc = umma_desc_sw128(a_addr);
+          const unsigned long long bdesc = umma_desc_sw128(a_addr + A_BYTES);
 #pragma unroll
-        for (int k4 = 0; k4 < BK / UK; ++k4)   // +32 bytes of K inside the swizzle atom = +2 in the address field
-          tc_mma_i8(tmem, adesc + (unsigned long long)(2 * k4), bdesc + (unsigned long long)(2 * k4), idesc,
-                    (unsigned)((ks | k4) != 0));
-        tc_commit(smem_u32(&s_empty[slot]));   // frees the stage when these MMAs have read it
+          for (int k4 = 0; k4 < BK / UK; ++k4)   // +32 bytes of K inside the swizzle atom = +2 in the address field
+            tc_mma_i8(acc, adesc + (unsigned long long)(2 * k4), bdesc + (unsigned long long)(2 * k4), idesc,
+                      (unsigned)((ks | k4) != 0));
+          tc_commit(smem_u32(&s_empty[slot]));   // frees the stage when these MMAs have read it
+        }
+        tc_commit(smem_u32(&s_acc_full[ab]));    // accumulator complete
       }
-      tc_commit(smem_u32(&s_acc));             // accumulator complete
     }
   } else {
     // epilogue: warp w may touch TMEM lanes [32 (w % 4), +32)
     const int quad = warp & 3;
-    const int grow = col_i + quad * 32 + lane;   // row i of the Gram (column index of A)
-    mbar_wait(smem_u32(&s_acc), 0);
-    tc_fence_after();
-    long long* tab = p.table + (size_t)t * p.kp * p.kp;
-    for (int c0 = 0; c0 < n_mma; c0 += 32) {
-      if (col_j + c0 > col_i + BM - 1) break;    // the rest of the tile lies above the diagonal
-      unsigned v[32];
-      tc_ld32(tmem + ((unsigned)(quad * 32) << 16) + (unsigned)c0, v);
+    unsigned nu = 0;
+    for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x, ++nu) {
+      const Unit u = decode_unit(p, unit);
+      const unsigned ab = nu & 1;
+      const int grow = u.col_i + quad * 32 + lane;   // row i of the Gram (column index of A)
+      mbar_wait(smem_u32(&s_acc_full[ab]), (nu >> 1) & 1);
+      tc_fence_after();
+      long long* tab = p.table + (size_t)u.t * p.kp * p.kp;
+      for (int c0 = 0; c0 < u.n_mma; c0 += 32) {
+        if (u.col_j + c0 > u.col_i + BM - 1) break;    // the rest of the tile lies above the diagonal
+        unsigned v[32];
+        tc_ld32(tmem + ((unsigned)(quad * 32) << 16) + ab * BN + (unsigned)c0, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int gcol = col_j + c0 + j;
-        if (grow < p.ka && gcol <= grow && nks > 0)
-          atomicAdd(reinterpret_cast<unsigned long long*>(tab + (size_t)gcol * p.kp + grow),
-                    (unsigned long long)(long long)(int)v[j]);
+        for (int j = 0; j < 32; ++j) {
+          const int gcol = u.col_j + c0 + j;
+          if (grow < p.ka && gcol <= grow && u.nks > 0)
+            atomicAdd(reinterpret_cast<unsigned long long*>(tab + (size_t)gcol * p.kp + grow),
+                      (unsigned long long)(long long)(int)v[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        unsigned long long st;
+        asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(smem_u32(&s_acc_empty[ab])) : "memory");
       }
     }
   }
@@ -578,8 +625,9 @@ I8Plan plan_i8(int64_t n_rows, int k) {
   pl.off_colmax = 0;
   pl.off_flag = align256((size_t)pl.ka * sizeof(unsigned long long));
   pl.off_table = pl.off_flag + 256;
-  pl.off_planes = pl.off_table + align256((size_t)NMOD * pl.kp * pl.kp * sizeof(long long));
-  pl.total = pl.off_planes + align256((size_t)NMOD * pl.kpc * (size_t)pl.ldr) + 1024;
+  size_t off = pl.off_table + align256((size_t)NMOD * pl.kp * pl.kp * sizeof(long long));
+  pl.off_planes = (off + 1023) & ~(size_t)1023;
+  pl.total = pl.off_planes + align256((size_t)NMOD * pl.kpc * (size_t)pl.ldr) + 1024;   // + slack to align the base
   return pl;
 }
 
@@ -589,19 +637,21 @@ bool fsb_gram_i8_available() { return get_encode() != nullptr; }
 
 size_t fsb_gram_i8_ws_bytes(int64_t n_rows, int k) { return plan_i8(n_rows, k).total; }
 
-// `weff` already carries the test mask (weight 0); `ws` must be 256-byte aligned and zero-initialised
-// by this function where needed.  gaug is fully overwritten.
+// `weff` already carries the test mask (weight 0).  gaug is fully overwritten.  Everything runs on `s`.
+// (A two-stream version that converted slab i+1 beside the tensor-core kernel of slab i was measured: the
+// kernels do share SMs once the GEMM is persistent and both ask for the same shared-memory carve-out, but the
+// conversion then runs at ~40 % speed and the carve-out costs it 20 % when alone -- no net gain, so the slabs
+// are processed back to back.)
 int fsb_launch_gram_i8(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* weff,
                        int64_t n_rows, int k, double* gaug, void* ws, size_t ws_bytes, cudaStream_t s) {
   const I8Plan pl = plan_i8(n_rows, k);
   if (ws_bytes < pl.total) return FSB_ERR_WORKSPACE_TOO_SMALL;
   if (!get_encode()) return FSB_ERR_UNSUPPORTED;
-  char* base = (char*)ws;
+  char* base = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
   unsigned long long* colmax = (unsigned long long*)(base + pl.off_colmax);
   int* flag = (int*)(base + pl.off_flag);
   long long* table = (long long*)(base + pl.off_table);
   char* planes = base + pl.off_planes;
-  planes = (char*)(((uintptr_t)planes + 1023) & ~(uintptr_t)1023);
   const int ka = pl.ka;
   const int beta = 53;
 
@@ -613,14 +663,13 @@ int fsb_launch_gram_i8(const fsb_context* h, const double* A, int64_t lda, const
   }
   static bool attr_set = false;
   const size_t gemm_smem = (size_t)NST * STAGE_BYTES + 1024;
-  const size_t cv_smem = (size_t)NMOD * CV_COLS * 33 * sizeof(unsigned);
   if (!attr_set) {
     FSB_CUDA_TRY(cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
-    FSB_CUDA_TRY(cudaFuncSetAttribute(i8_convert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv_smem));
     attr_set = true;
   }
-  int first = 1;
-  for (int64_t r0 = 0; r0 < n_rows; r0 += pl.slab_rows) {
+  const int64_t nslab = fsb_ceil_div(n_rows, pl.slab_rows);
+  for (int64_t i = 0; i < nslab; ++i) {
+    const int64_t r0 = i * pl.slab_rows;
     const int64_t nr = (n_rows - r0) < pl.slab_rows ? (n_rows - r0) : pl.slab_rows;
     const double* As = A + r0 * lda;
     const double* bs = b + r0;
@@ -635,8 +684,8 @@ int fsb_launch_gram_i8(const fsb_context* h, const double* A, int64_t lda, const
     }
     {
       dim3 grid((unsigned)(pl.kpc / CV_COLS), (unsigned)fsb_ceil_div(nr, CV_ROWS));
-      i8_convert_kernel<<<grid, CV_THREADS, cv_smem, s>>>(As, lda, bs, ws_, nr, k, colmax, beta, (unsigned*)planes,
-                                                          pl.ldr, pl.kpc);
+      i8_convert_kernel<<<grid, CV_THREADS, 0, s>>>(As, lda, bs, ws_, nr, k, colmax, beta, (unsigned*)planes, pl.ldr,
+                                                    pl.kpc);
       FSB_LAUNCH_CHECK("i8_convert_kernel");
     }
     {
@@ -651,22 +700,23 @@ int fsb_launch_gram_i8(const fsb_context* h, const double* A, int64_t lda, const
       if (cr != CUDA_SUCCESS) return FSB_ERR_UNSUPPORTED;
       GemmArgs ga;
       ga.n_i = pl.n_i; ga.ntile = pl.ntile; ga.ka = ka; ga.kp = pl.kp; ga.slab_rows = nr; ga.table = table;
-      // enough units for ~8 waves, each between 4096 and 65536 rows
+      // enough units for ~8 per SM, each between 4096 and 65536 rows
       int64_t want_chunks = fsb_ceil_div((int64_t)h->sm_count * 8, (int64_t)pl.ntile * NMOD);
       int64_t ur = fsb_round_up(fsb_ceil_div(nr, want_chunks), BK);
       if (ur < 4096) ur = 4096;
       if (ur > UNIT_ROWS_MAX) ur = UNIT_ROWS_MAX;
       ga.unit_rows = ur;
       const int64_t nchunk = fsb_ceil_div(nr, ur);
-      i8_gemm_kernel<<<(unsigned)(nchunk * NMOD * pl.ntile), GEMM_THREADS, gemm_smem, s>>>(tmap, ga);
+      ga.nunits = (int)(nchunk * NMOD * pl.ntile);
+      const int grid = ga.nunits < h->sm_count ? ga.nunits : h->sm_count;
+      i8_gemm_kernel<<<(unsigned)grid, GEMM_THREADS, gemm_smem, s>>>(tmap, ga);
       FSB_LAUNCH_CHECK("i8_gemm_kernel");
     }
     {
       dim3 grid((unsigned)fsb_ceil_div(ka, 128), (unsigned)ka);
-      i8_crt_kernel<<<grid, 128, 0, s>>>(table, pl.kp, ka, colmax, beta, flag, first, gaug);
+      i8_crt_kernel<<<grid, 128, 0, s>>>(table, pl.kp, ka, colmax, beta, flag, i == 0 ? 1 : 0, gaug);
       FSB_LAUNCH_CHECK("i8_crt_kernel");
     }
-    first = 0;
   }
   return FSB_OK;
 }
