@@ -206,6 +206,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--gram-path", default="auto", choices=["auto", "fp64", "int8"],
+                    help="Gram arithmetic: fp64 DMMA, int8 tcgen05 (exact integer, CRT), or the library's choice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -230,6 +232,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         group = dist.group.WORLD
     eng = Engine(local)
+    eng.set_gram_path(args.gram_path)
     dev = eng.device
     hbm_peak, bf16_peak, peak_kind = load_peaks()
 
@@ -418,26 +421,44 @@ def main():
     if rank == 0:
         flops = (2.0 * k * k + 2.0 * k) * n_rows
         achieved = flops / (gram_ms * 1e-3) / 1e12
+        gram_path = eng.gram_path(n_rows, k)
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s",
+                    "frac": achieved / bf16_peak, "traffic": None,
+                    "peak_kind": "dense bf16 cuBLAS, %s (MEASURED_PEAKS.json)" % peak_kind,
+                    "achieved_kind": "algorithmic fp64 flops (2k^2+2k per row, full Gram convention) / Gram time",
+                    "hbm_gbs_during_gram": 8.0 * (k + 2) * n_rows / (gram_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak}
+        if gram_path == "int8":
+            n_i = -(-(k + 1) // 128)
+            ops = sum(2.0 * 128 * (256 if 2 * jj + 1 < n_i else 128) * n_rows * 16
+                      for i_ in range(n_i) for jj in range(i_ // 2 + 1))
+            roofline.update({
+                "kernel": "i8_gemm_kernel (tcgen05.mma kind::i8) + i8_colmax/i8_convert/i8_crt_kernel",
+                "int8_top_s_executed_over_whole_gram": ops / (gram_ms * 1e-3) / 1e12,
+                "note": "fp64 Gram recast as 16 exact int8 GEMMs modulo coprime moduli (CRT); the tcgen05 kernel "
+                        "alone keeps the tensor pipe ~84 % busy (profiles/r01_i8_*.txt); the Gram time also holds "
+                        "the column-maximum, residue-conversion and CRT passes"})
+        else:
+            roofline.update({
+                "kernel": ("gram_rowsplit_kernel" if k + 1 <= 104 else
+                           ("gram_dmma_kernel" if k + 1 <= 128 else "preweight_kernel + gram_tma_kernel")) +
+                          " (+gram_reduce_kernel)",
+                "fp64_note": "tcgen05 has no f64 kind; this kernel runs on DMMA.8x8x4 whose measured peak on this "
+                             "pool is 37.1 TFLOP/s (tools/ubench/fp64_rates.cu): frac_of_fp64_peak = %.3f "
+                             "(algorithmic flops count the full K x K Gram, the kernel executes the lower "
+                             "triangle only)" % (achieved / 37.1)})
         line = {
             "metric": "design_matrix_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload + ": " + wl["desc"], "rows_per_gpu": n_rows, "k": k,
                        "configs_per_gpu": ncfg, "atoms_per_config": n, "alpha": ALPHA, "refine_rounds": REFINE,
+                       "gram_path": gram_path,
                        "parallelism": "row-shard x%d, 1 all-reduce of (k+1)^2 + %d of k doubles" % (world, REFINE),
                        "l2": "inputs (A %.0f MB + raw %.0f MB per GPU) larger than the 126 MB L2; no flush" %
                              (n_rows * k * 8 / 1e6, n_rows * (kraw + 1) * 8 / 1e6)},
             "gram_tflops_algorithmic": achieved,
             "gram_ms": gram_ms,
-            "roofline": {"kernel": ("gram_rowsplit_kernel" if k + 1 <= 104 else ("gram_dmma_kernel" if k + 1 <= 128 else "preweight_kernel + gram_tma_kernel")) + " (+gram_reduce_kernel)", "bound": "tensor", "achieved": achieved,
-                         "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak, "traffic": None,
-                         "peak_kind": "dense bf16 cuBLAS, %s (MEASURED_PEAKS.json)" % peak_kind,
-                         "fp64_note": "tcgen05 has no f64 kind; this kernel runs on DMMA.8x8x4 whose measured peak "
-                                      "on this pool is 37.1 TFLOP/s (tools/ubench/fp64_rates.cu): frac_of_fp64_peak "
-                                      "= %.3f (algorithmic flops count the full K x K Gram, the kernel executes "
-                                      "the lower triangle only)" % (achieved / 37.1),
-                         "hbm_gbs_during_gram": 8.0 * (k + 2) * n_rows / (gram_ms * 1e-3) / 1e9,
-                         "hbm_peak_gbs": hbm_peak},
+            "roofline": roofline,
             "coeff_max_rel_err": coeff_err,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,

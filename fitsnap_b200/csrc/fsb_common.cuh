@@ -45,8 +45,9 @@ constexpr int FSB_GLDS = FSB_GT + 4; // smem row pitch in doubles: == 4 (mod 16)
 constexpr int FSB_GTHREADS = 512;    // 16 warps, each owning a 32x32 sub-tile (4x4 DMMA 8x8 blocks)
 
 // FSB_GRAM_AUTO switches to the int8 tcgen05 Gram from this shape on (gram.cu: fsb_gram_path_for)
-constexpr int FSB_I8_AUTO_MIN_COLS = 1 << 30;   // not enabled by default yet
-constexpr int64_t FSB_I8_AUTO_MIN_ROWS = 65536;
+// (measured crossover against the DMMA path: ~250 columns; 1.7x at 480, 2.3x at 1000 columns)
+constexpr int FSB_I8_AUTO_MIN_COLS = 384;
+constexpr int64_t FSB_I8_AUTO_MIN_ROWS = 32768;
 
 // Cholesky panel width
 constexpr int FSB_NB = 64;

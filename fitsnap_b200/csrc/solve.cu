@@ -13,6 +13,9 @@
 //   L[kp*kp]   row-major, pitch kp; lower triangle holds the Cholesky factor of S = D (G+alpha I) D
 //   Linv[kp*32] (k <= 128) inverses of the 32x32 diagonal blocks of L: the small solve is then four
 //              block steps of tiny mat-vecs instead of k dependent scalar steps
+//   Linv[kp2*kp2] (k > 128) the explicit inverse of L (lower triangle, pitch kp2 = 64 * next power of two of
+//              kp/64), built once per factorisation by block doubling (batched 64x64-tile GEMMs); every solve /
+//              refinement step is then two GEMVs spread over the whole GPU instead of a single-CTA substitution
 //
 // The factorisation is a right-looking blocked Cholesky with 64-wide panels, three small
 // kernels per panel (diag potrf / panel trsm / trailing syrk).  k <= 1024 means <= 48
@@ -20,6 +23,7 @@
 // Gram pass, so it is written for robustness, not peak.
 #include "fsb_common.cuh"
 #include <float.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -30,8 +34,9 @@ struct FactorView {
   double* d;
   double* flag;
   double* L;
-  double* Linv;   // k <= 128 only: inverses of the 32x32 diagonal blocks of L, [kp/32][32][32]
+  double* Linv;   // k <= 128: inverses of the 32x32 diagonal blocks of L, [kp/32][32][32]; else L^-1, pitch kp2
   int kp;
+  int kp2;        // pitch of the explicit inverse (k > 128)
 };
 
 __host__ __device__ inline FactorView view_factor(void* buf, int k) {
@@ -42,6 +47,9 @@ __host__ __device__ inline FactorView view_factor(void* buf, int k) {
   v.flag = v.d + v.kp;
   v.L = v.flag + v.kp;
   v.Linv = v.L + (size_t)v.kp * v.kp;
+  int np2 = 1;
+  while (np2 * NB < v.kp) np2 *= 2;
+  v.kp2 = np2 * NB;
   return v;
 }
 
@@ -517,6 +525,159 @@ __global__ void __launch_bounds__(SMALL_K) small_solve_kernel(FactorView f, int 
   for (int i = tid; i < k; i += nt) x_out[i] = (x_in ? x_in[i] : 0.0) + f.d[i] * y[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Large systems (k > 128): explicit inverse of the Cholesky factor by block doubling.
+//   level 0   Linv_pp = L_pp^-1 for every 64x64 diagonal block (one CTA each, thread per column)
+//   level l   blocks of size s = 64 2^l are paired:  Linv21 = -Linv22 (L21 Linv11)
+//             as two batched tile GEMMs; the intermediate T = Linv22 L21 lives in the (unused) mirror
+//             block of the upper triangle.  Zero blocks of the triangular operands are skipped.
+// Dropped columns (flag) need no special care here: their column of L is e_c, and the solve masks y_c.
+__global__ void __launch_bounds__(NB) trtri_diag_kernel(FactorView f) {
+  __shared__ double l[NB][NBP];
+  const int p = blockIdx.x, kp = f.kp;
+  const double* blk = f.L + (size_t)(p * NB) * kp + p * NB;
+  for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
+    const int r = idx / NB, c = idx % NB;
+    l[r][c] = __ldg(blk + (size_t)r * kp + c);
+  }
+  __syncthreads();
+  // column j of the inverse: forward substitution on e_j, kept in registers
+  const int j = threadIdx.x;
+  double x[NB];
+#pragma unroll
+  for (int r = 0; r < NB; ++r) x[r] = (r == j) ? 1.0 : 0.0;
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    const double xr = (r >= j) ? x[r] / l[r][r] : 0.0;
+    x[r] = xr;
+#pragma unroll
+    for (int r2 = r + 1; r2 < NB; ++r2) x[r2] -= xr * l[r2][r];
+  }
+  double* out = f.Linv + (size_t)(p * NB) * f.kp2 + p * NB;
+#pragma unroll
+  for (int r = 0; r < NB; ++r) out[(size_t)r * f.kp2 + j] = x[r];
+}
+
+// one 64x64 tile of  C = sign * A B  with A (64 x 64 nkb) and B (64 nkb x 64) given by pointers + pitches;
+// rows/columns of A or B at or beyond `a_lim` / `b_lim` (global indices kept by the caller) read as zero
+struct TileGemm {
+  const double* a; int64_t lda;
+  const double* b; int64_t ldb;
+  double* c; int64_t ldc;
+  int kb0, kb1;     // 64-wide k blocks [kb0, kb1)
+  double sign;
+  bool a_zero;      // the A tile lies outside the stored matrix: the product is zero
+};
+
+__device__ __forceinline__ void tile_gemm(const TileGemm& g) {
+  constexpr int MH = 16;
+  __shared__ double sa[NB][MH + 1];
+  __shared__ double sb[MH][NB + 1];
+  const int tr = (threadIdx.x / 16) * 4, tc = (threadIdx.x % 16) * 4;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  if (!g.a_zero) {
+    for (int m0 = g.kb0 * NB; m0 < g.kb1 * NB; m0 += MH) {
+      for (int idx = threadIdx.x; idx < NB * MH; idx += blockDim.x) {
+        const int r = idx / MH, c = idx % MH;
+        sa[r][c] = g.a[(size_t)r * g.lda + m0 + c];
+        const int r2 = idx / NB, c2 = idx % NB;
+        sb[r2][c2] = g.b[(size_t)(m0 + r2) * g.ldb + c2];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < MH; ++m) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = sa[tr + i][m]; b[i] = sb[m][tc + i]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g.c[(size_t)(tr + i) * g.ldc + tc + j] = g.sign * acc[i][j];
+}
+
+// step 1 of a level: T = Linv22 * L21 (Linv22 lower triangular: k blocks 0..ti), T stored in the mirror block
+// step 2:            Linv21 = -T * Linv11 (Linv11 lower triangular: k blocks tj..nb-1)
+template <int STEP>
+__global__ void __launch_bounds__(256) trtri_level_kernel(FactorView f, int nb) {
+  // grid: x = tile (ti * nb + tj) inside the s x s block, y = pair
+  const int ti = blockIdx.x / nb, tj = blockIdx.x % nb;
+  const int base = blockIdx.y * 2 * nb;               // first 64-block of the pair
+  const int np = f.kp / NB;
+  const int64_t p2 = f.kp2;
+  TileGemm g;
+  const int r1 = base + nb;                           // block row of the "2" half
+  if (STEP == 1) {
+    g.a = f.Linv + (size_t)((r1 + ti) * NB) * p2 + (size_t)r1 * NB;     g.lda = p2;
+    g.b = f.L + (size_t)(r1 * NB) * f.kp + (size_t)(base + tj) * NB;    g.ldb = f.kp;
+    g.c = f.Linv + (size_t)((base + ti) * NB) * p2 + (size_t)(r1 + tj) * NB;   g.ldc = p2;   // mirror block
+    g.kb0 = 0; g.kb1 = ti + 1;
+    g.sign = 1.0;
+    g.a_zero = (r1 + ti >= np);                       // rows of L beyond the matrix: L21 = 0 there
+    if (r1 + g.kb1 > np) g.kb1 = np - r1 > 0 ? np - r1 : 0;   // k blocks of L21 that exist
+    if (g.kb1 <= g.kb0) g.a_zero = true;
+  } else {
+    g.a = f.Linv + (size_t)((base + ti) * NB) * p2 + (size_t)r1 * NB;   g.lda = p2;           // T
+    g.b = f.Linv + (size_t)(base * NB) * p2 + (size_t)(base + tj) * NB; g.ldb = p2;
+    g.c = f.Linv + (size_t)((r1 + ti) * NB) * p2 + (size_t)(base + tj) * NB;   g.ldc = p2;
+    g.kb0 = tj; g.kb1 = nb;
+    g.sign = -1.0;
+    g.a_zero = (r1 + ti >= np);
+  }
+  tile_gemm(g);
+}
+
+// y = mask(Linv * D (rhs - alpha x_in)): warp per row
+__global__ void __launch_bounds__(256) inv_forward_kernel(FactorView f, int k, const double* __restrict__ rhs,
+                                                          int64_t rhs_stride, double alpha,
+                                                          const double* __restrict__ x_in, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= f.kp) return;
+  const double* lr = f.Linv + (size_t)row * f.kp2;
+  double part = 0.0;
+  for (int c = lane; c <= row && c < k; c += 32) {
+    const double xi = x_in ? x_in[c] : 0.0;
+    part += lr[c] * (f.d[c] * (rhs[(size_t)c * rhs_stride] - alpha * xi));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) y[row] = (row < k && f.flag[row] == 0.0) ? part : 0.0;
+}
+
+// x_out = x_in + D Linv^T y: 32 columns per CTA, 8 warps split the rows, fixed-order combine
+__global__ void __launch_bounds__(256) inv_backward_kernel(FactorView f, int k, const double* __restrict__ y,
+                                                           const double* __restrict__ x_in,
+                                                           double* __restrict__ x_out) {
+  __shared__ double part[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  double acc = 0.0;
+  if (col < k)
+    for (int r = blockIdx.x * 32 + warp; r < k; r += 8)
+      if (r >= col) acc += f.Linv[(size_t)r * f.kp2 + col] * y[r];
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && col < k) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += part[q][lane];
+    const double xi = x_in ? x_in[col] : 0.0;
+    x_out[col] = xi + f.d[col] * t;
+  }
+}
+
 __global__ void init_info_kernel(int32_t* info, int k) {
   if (threadIdx.x < FSB_INFO_LEN) info[threadIdx.x] = (threadIdx.x == FSB_INFO_FIRST_BAD_COLUMN) ? k : 0;
 }
@@ -526,7 +687,11 @@ __global__ void init_info_kernel(int32_t* info, int k) {
 size_t fsb_factor_bytes_impl(int k) {
   int kp = ((k + NB - 1) / NB) * NB;
   if (kp == 0) kp = NB;
-  return ((size_t)2 * kp + (size_t)kp * kp + (size_t)kp * 32) * sizeof(double);
+  if (k <= SMALL_K) return ((size_t)2 * kp + (size_t)kp * kp + (size_t)kp * 32) * sizeof(double);
+  int np2 = 1;
+  while (np2 * NB < kp) np2 *= 2;
+  const size_t kp2 = (size_t)np2 * NB;
+  return ((size_t)2 * kp + (size_t)kp * kp + kp2 * kp2 + (size_t)kp) * sizeof(double);   // d, flag, L, L^-1, y
 }
 
 int fsb_launch_factor(const fsb_context* h, const double* gaug, int k, double alpha, void* factor,
@@ -559,6 +724,18 @@ int fsb_launch_factor(const fsb_context* h, const double* gaug, int k, double al
       FSB_LAUNCH_CHECK("syrk_update_kernel");
     }
   }
+  // explicit inverse of L by block doubling
+  FSB_CUDA_TRY(cudaMemsetAsync(f.Linv, 0, (size_t)f.kp2 * f.kp2 * sizeof(double), s));
+  trtri_diag_kernel<<<np, NB, 0, s>>>(f);
+  FSB_LAUNCH_CHECK("trtri_diag_kernel");
+  for (int nb = 1; nb * NB < f.kp2; nb *= 2) {
+    const int pairs = f.kp2 / (2 * nb * NB);
+    dim3 grid((unsigned)(nb * nb), (unsigned)pairs);
+    trtri_level_kernel<1><<<grid, 256, 0, s>>>(f, nb);
+    FSB_LAUNCH_CHECK("trtri_level_kernel<1>");
+    trtri_level_kernel<2><<<grid, 256, 0, s>>>(f, nb);
+    FSB_LAUNCH_CHECK("trtri_level_kernel<2>");
+  }
   return FSB_OK;
 }
 
@@ -574,10 +751,18 @@ int fsb_launch_factor_solve(const fsb_context* h, const void* factor, int k, con
     FSB_LAUNCH_CHECK("small_solve_kernel");
     return FSB_OK;
   }
-  const size_t smem = ((size_t)f.kp + NB * NBP) * sizeof(double);
-  if (smem > h->smem_optin) return FSB_ERR_UNSUPPORTED;
-  FSB_CUDA_TRY(cudaFuncSetAttribute(trsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  trsv_kernel<<<1, 256, smem, s>>>(f, k, rhs, rhs_stride, alpha, x_in, x_out);
-  FSB_LAUNCH_CHECK("trsv_kernel");
+  if (getenv("FSB_SOLVE_TRSV")) {   // the single-CTA substitution, kept for cross-checking the inverse
+    const size_t smem = ((size_t)f.kp + NB * NBP) * sizeof(double);
+    if (smem > h->smem_optin) return FSB_ERR_UNSUPPORTED;
+    FSB_CUDA_TRY(cudaFuncSetAttribute(trsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trsv_kernel<<<1, 256, smem, s>>>(f, k, rhs, rhs_stride, alpha, x_in, x_out);
+    FSB_LAUNCH_CHECK("trsv_kernel");
+    return FSB_OK;
+  }
+  double* y = f.Linv + (size_t)f.kp2 * f.kp2;
+  inv_forward_kernel<<<(unsigned)fsb_ceil_div(f.kp, 8), 256, 0, s>>>(f, k, rhs, rhs_stride, alpha, x_in, y);
+  FSB_LAUNCH_CHECK("inv_forward_kernel");
+  inv_backward_kernel<<<(unsigned)fsb_ceil_div(k, 32), 256, 0, s>>>(f, k, y, x_in, x_out);
+  FSB_LAUNCH_CHECK("inv_backward_kernel");
   return FSB_OK;
 }

@@ -156,7 +156,13 @@ class Engine:
         _cabi.check("fsb_factor", self.lib.fsb_factor(self._h, _ptr(gaug), k, float(alpha), _ptr(buf), nbytes,
                                                        _ptr(info), self._stream()))
         npanel = (k + 63) // 64
-        self.launch_count += 1 if k <= 128 else 2 + npanel + 2 * max(npanel - 1, 0)
+        if k <= 128:
+            self.launch_count += 1
+        else:
+            # init + equilibrate + blocked Cholesky (potrf / trsm / syrk per panel) + explicit inverse of L
+            # (diagonal blocks, then two tile-GEMM launches per doubling level)
+            levels = max(0, (npanel - 1).bit_length())
+            self.launch_count += 2 + npanel + 2 * max(npanel - 1, 0) + 1 + 2 * levels
         return Factor(buf, info, k, float(alpha))
 
     def solve(self, factor, rhs, rhs_stride=1, x_in=None, out=None):
@@ -165,7 +171,7 @@ class Engine:
         _cabi.check("fsb_factor_solve",
                     self.lib.fsb_factor_solve(self._h, _ptr(factor.buf), k, _ptr(rhs), int(rhs_stride),
                                               factor.alpha, _ptr(x_in), _ptr(x), self._stream()))
-        self.launch_count += 1
+        self.launch_count += 1 if k <= 128 else 2      # k > 128: forward + backward GEMV with the explicit inverse
         return x
 
     def pinv_factor(self, gaug, rcond=None):
