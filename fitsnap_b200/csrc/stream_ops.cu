@@ -125,6 +125,169 @@ __global__ void __launch_bounds__(256, MINB) rowpass_kernel(const double* __rest
   }
 }
 
+// ------------------------------------------------------------------------------ K7, bulk-copy staged
+// The register-staged kernel above is latency-bound for narrow rows (k ~ 100: 25 % occupancy, 4.7 TB/s):
+// its loads in flight are bounded by registers.  Here one producer thread streams tiles of BK_ROWS whole rows
+// -- contiguous in memory when lda == k -- into a shared-memory ring with cp.async.bulk (TMA 1-D, SASS
+// UBLKCP), completion on mbarriers; ~150-200 KB per SM are in flight at no register cost.  8 consumer warps
+// take 8 rows each per tile (lanes across columns, LDS), b / w / test flags of the NEXT tile are prefetched
+// into registers while the current one is processed.  Same arithmetic and the same fixed-order reduction as
+// rowpass_kernel<.., true>.
+constexpr int BK_ROWS = 64;
+constexpr int BK_CONSUMERS = 256;
+constexpr int BK_NW = BK_CONSUMERS / 32;          // consumer warps
+constexpr int BK_RPW = BK_ROWS / BK_NW;            // rows of a tile per warp
+constexpr int BK_THREADS = BK_CONSUMERS + 32;
+
+__device__ __forceinline__ unsigned bk_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bk_mbar_wait(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  for (unsigned spin = 0; spin < (1u << 24); ++spin) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(BK_THREADS, 1) rowpass_bulk_kernel(const double* __restrict__ A,
+                                                                     const double* __restrict__ b,
+                                                                     const double* __restrict__ w,
+                                                                     const uint8_t* __restrict__ testing,
+                                                                     int64_t n_rows, int k,
+                                                                     const double* __restrict__ x,
+                                                                     double* __restrict__ out, int64_t rows_per_cta,
+                                                                     int nstage) {
+  extern __shared__ __align__(128) unsigned char bk_raw[];
+  __shared__ __align__(8) unsigned long long s_full[8];
+  __shared__ __align__(8) unsigned long long s_empty[8];
+  double* ring = reinterpret_cast<double*>(bk_raw);              // nstage x (BK_ROWS x k)
+  const size_t stage_doubles = (size_t)BK_ROWS * k;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  int64_t r_end = r_begin + rows_per_cta;
+  if (r_end > n_rows) r_end = n_rows;
+  const int ntile = r_end > r_begin ? (int)((r_end - r_begin + BK_ROWS - 1) / BK_ROWS) : 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < nstage; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bk_smem_u32(&s_full[i])), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bk_smem_u32(&s_empty[i])), "r"(BK_NW) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == BK_CONSUMERS / 32) {
+    // ---- producer
+    if (lane == 0) {
+      for (int t = 0; t < ntile; ++t) {
+        const int slot = t % nstage, n = t / nstage;
+        if (t >= nstage) bk_mbar_wait(bk_smem_u32(&s_empty[slot]), (unsigned)((n - 1) & 1));
+        const int64_t r0 = r_begin + (int64_t)t * BK_ROWS;
+        const int nr = (int)((r_end - r0) < BK_ROWS ? (r_end - r0) : BK_ROWS);
+        const unsigned bytes = (unsigned)((size_t)nr * k * sizeof(double));
+        const unsigned full = bk_smem_u32(&s_full[slot]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(bk_smem_u32(ring + slot * stage_doubles)), "l"(A + r0 * k), "r"(bytes), "r"(full)
+                     : "memory");
+      }
+    }
+    return;
+  }
+
+  // ---- consumers
+  double xr[NPL], gacc[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int c = lane + 32 * i;
+    xr[i] = (c < k) ? x[c] : 0.0;
+    gacc[i] = 0.0;
+  }
+  // lane q < BK_RPW keeps (w, b) of row BK_RPW * warp + q of the tile; test rows and rows past the end get w = 0
+  auto fetch = [&](int t, double& wv, double& bv) {
+    wv = 0.0; bv = 0.0;
+    const int64_t r = r_begin + (int64_t)t * BK_ROWS + warp * BK_RPW + (lane & (BK_RPW - 1));
+    if (t < ntile && r < r_end) {
+      bv = __ldg(b + r);
+      const double ww = __ldg(w + r);
+      wv = (testing && __ldg(testing + r)) ? 0.0 : ww;
+    }
+  };
+  double w_cur, b_cur, w_nxt, b_nxt;
+  fetch(0, w_cur, b_cur);
+  for (int t = 0; t < ntile; ++t) {
+    fetch(t + 1, w_nxt, b_nxt);
+    const int slot = t % nstage, n = t / nstage;
+    bk_mbar_wait(bk_smem_u32(&s_full[slot]), (unsigned)(n & 1));
+    const double* tile = ring + slot * stage_doubles + (size_t)(warp * BK_RPW) * k;
+    const int64_t r0 = r_begin + (int64_t)t * BK_ROWS + warp * BK_RPW;
+    // branch-free over the warp's rows (rows past the end: weight 0 and the stale tile bytes are replaced by 0), in two
+    // groups of 4 so that the loads, dots and shuffles of independent rows interleave
+#pragma unroll
+    for (int q0 = 0; q0 < BK_RPW; q0 += 4) {
+      double a[4][NPL], wv[4], bv[4], dot[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        wv[q] = __shfl_sync(0xffffffffu, w_cur, q0 + q);
+        bv[q] = __shfl_sync(0xffffffffu, b_cur, q0 + q);
+        const bool valid = r0 + q0 + q < r_end;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const int c = lane + 32 * i;
+          const double v = (c < k) ? tile[(q0 + q) * k + c] : 0.0;
+          a[q][i] = valid ? v * wv[q] : 0.0;             // aw = w * a, rounded as the reference does (svd.py:44)
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        dot[q] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) dot[q] += a[q][i] * xr[i];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dot[q] += __shfl_xor_sync(0xffffffffu, dot[q], o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double res = wv[q] * bv[q] - dot[q];       // bw - aw x
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) gacc[i] += a[q][i] * res;
+      }
+    }
+    __syncwarp();
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bk_smem_u32(&s_empty[slot])) : "memory");
+    w_cur = w_nxt; b_cur = b_nxt;
+  }
+
+  // fixed-order reduction over the consumer warps (the ring is free now: all tiles consumed by this warp,
+  // other warps may still read theirs -> use a separate region past the ring)
+  double* sg = ring + (size_t)nstage * stage_doubles;      // BK_NW x k doubles
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int c = lane + 32 * i;
+    if (c < k) sg[warp * k + c] = gacc[i];
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(BK_CONSUMERS) : "memory");
+  for (int c = tid; c < k; c += BK_CONSUMERS) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < BK_NW; ++q) t += sg[q * k + c];
+    out[(size_t)blockIdx.x * k + c] = t;
+  }
+}
+
 // Deterministic column sums of the per-CTA partial vectors: 32 columns x 32 part-groups per block,
 // each group adds its parts in index order, the 32 group sums are combined in a fixed order.
 __global__ void __launch_bounds__(1024) colsum_reduce_kernel(const double* __restrict__ partial, int nparts, int k,
@@ -237,6 +400,43 @@ RowPlan plan_rows(const fsb_context* h, int64_t n_rows) {
   pl.rows_per_cta = fsb_ceil_div(n_rows > 0 ? n_rows : 1, want);
   pl.ncta = (int)fsb_ceil_div(n_rows > 0 ? n_rows : 1, pl.rows_per_cta);
   return pl;
+}
+
+// bulk-copy staged residual pass: whole rows must be contiguous (lda == k) and 16-byte tileable
+bool rowpass_bulk_ok(const fsb_context* h, const double* A, int64_t lda, int64_t n_rows, int k) {
+  static int off = -1;
+  if (off < 0) off = getenv("FSB_ROWPASS_NO_BULK") ? 1 : 0;
+  return !off && lda == k && (k & 1) == 0 && k <= 128 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+         n_rows >= (int64_t)h->sm_count * BK_ROWS * 4;
+}
+
+int launch_rowpass_bulk(const fsb_context* h, const double* A, const double* b, const double* w,
+                        const uint8_t* testing, int64_t n_rows, int k, const double* x, double* out, int* nparts,
+                        cudaStream_t s) {
+  const size_t stage = (size_t)BK_ROWS * k * sizeof(double);
+  const size_t tail = (size_t)BK_NW * k * sizeof(double);
+  int nstage = (int)((h->smem_optin - 2048 - tail) / stage);
+  if (nstage > 6) nstage = 6;
+  if (nstage < 2) return FSB_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)nstage * stage + tail;
+  const int grid = h->sm_count;
+  const int64_t rows_per_cta = fsb_round_up(fsb_ceil_div(n_rows, grid), BK_ROWS);
+  const int npl = (k + 31) / 32;
+#define FSB_BULK(NPL)                                                                                          \
+  do {                                                                                                         \
+    FSB_CUDA_TRY(cudaFuncSetAttribute(rowpass_bulk_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                      (int)smem));                                                             \
+    rowpass_bulk_kernel<NPL><<<grid, BK_THREADS, smem, s>>>(A, b, w, testing, n_rows, k, x, out, rows_per_cta, \
+                                                            nstage);                                           \
+  } while (0)
+  if (npl <= 1) FSB_BULK(1);
+  else if (npl <= 2) FSB_BULK(2);
+  else if (npl <= 4) FSB_BULK(4);
+  else FSB_BULK(8);
+#undef FSB_BULK
+  FSB_LAUNCH_CHECK("rowpass_bulk_kernel");
+  *nparts = grid;
+  return FSB_OK;
 }
 
 template <bool WITH_G>
@@ -498,9 +698,14 @@ int fsb_launch_residual(const fsb_context* h, const double* A, int64_t lda, cons
                         size_t ws_bytes, cudaStream_t s) {
   RowPlan pl = plan_rows(h, n_rows);
   if (ws_bytes < (size_t)pl.ncta * k * sizeof(double)) return FSB_ERR_WORKSPACE_TOO_SMALL;
-  int st = launch_rowpass<true>(h, A, lda, b, w, testing, n_rows, k, x, (double*)ws, s);
+  int nparts = pl.ncta;
+  int st;
+  if (rowpass_bulk_ok(h, A, lda, n_rows, k) && h->sm_count <= pl.ncta)
+    st = launch_rowpass_bulk(h, A, b, w, testing, n_rows, k, x, (double*)ws, &nparts, s);
+  else
+    st = launch_rowpass<true>(h, A, lda, b, w, testing, n_rows, k, x, (double*)ws, s);
   if (st != FSB_OK) return st;
-  colsum_reduce_kernel<<<(unsigned)fsb_ceil_div(k, 32), 1024, 0, s>>>((const double*)ws, pl.ncta, k, g);
+  colsum_reduce_kernel<<<(unsigned)fsb_ceil_div(k, 32), 1024, 0, s>>>((const double*)ws, nparts, k, g);
   FSB_LAUNCH_CHECK("colsum_reduce_kernel");
   return FSB_OK;
 }

@@ -250,6 +250,26 @@ def test_residual_and_predict(engine):
         assert np.max(np.abs(y - lf.predictions(a, x))) <= 1e-13 * np.abs(a).sum(1).max() * np.abs(x).max()
 
 
+@pytest.mark.parametrize("n,k", [(40001, 100), (60000, 30), (38912, 128), (50007, 64)])
+def test_residual_bulk_staged_kernel(engine, n, k):
+    """Even, contiguous row widths with enough rows take the cp.async.bulk staged kernel (stream_ops.cu):
+    same result as the oracle, odd row counts / ragged last tile / test mask included, deterministic."""
+    rng = np.random.default_rng(n + k)
+    a = rng.standard_normal((n, k))
+    b, w = rng.standard_normal(n), 10.0 ** rng.uniform(-1, 1, n)
+    t = rng.random(n) < 0.2
+    x = rng.standard_normal(k)
+    A, B, W, T = dev(engine, a, b, w, t)
+    X = engine.to_device(x)
+    for tt, TT in ((t, T), (None, None)):
+        aw, bw = lf.weighted_system(a, b, w, tt)
+        g_ref = aw.T @ (bw - aw @ x)
+        g = engine.residual(A, B, W, TT, X)
+        assert torch.equal(g, engine.residual(A, B, W, TT, X))
+        bound = 1e-12 * np.max(np.abs(aw).sum(0)) * (np.abs(bw).max() + np.abs(aw @ x).max())
+        assert np.max(np.abs(g.cpu().numpy() - g_ref)) <= bound
+
+
 def test_rank_deficient_duplicate_column_is_reported(engine):
     rng = np.random.default_rng(4)
     a = rng.standard_normal((500, 10))
