@@ -335,6 +335,30 @@ def main():
     gram_ms = float(np.mean([a_.elapsed_time(b_) for a_, b_ in gram_ev]))
     value = world * n_rows / (ms_step / 1e3)
 
+    # ---- the same step replayed from a CUDA graph (one cudaGraphLaunch instead of `launches` launches) ----
+    graph_info = None
+    try:
+        cap = pipe.capture(batch, None, out)
+        for _ in range(3):
+            cap.replay()
+        torch.cuda.synchronize()
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(args.steps):
+            rg = cap.replay()
+        q1.record()
+        torch.cuda.synchronize()
+        barrier()
+        tg = torch.tensor([q0.elapsed_time(q1) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX, group=group)
+        graph_info = {"ms_per_step": float(tg.item()), "rows_per_s": world * n_rows / (float(tg.item()) / 1e3),
+                      "kernels_per_replay": int(cap.launches),
+                      "same_x_as_eager": bool(torch.equal(rg.x, x))}
+    except Exception as exc:                      # report, never hide: the eager numbers above stand on their own
+        graph_info = {"error": repr(exc)[:200]}
+
     # ---- parity of the timed path: coefficients vs the oracle on the SAME (A, b, w) (rank 0, N=1) --
     coeff_err = None
     cpu_baseline = None
@@ -463,6 +487,7 @@ def main():
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "gpu_launches": int(launches),
+            "cuda_graph_replay": graph_info,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -41,6 +41,10 @@ class LinearFitPipeline:
         res.extra.update(A=A, b=b, w=w, nonfinite=bad)
         return res
 
+    def capture(self, batch: ConfigBatch, testing=None, out=None, warmup=2) -> "CapturedStep":
+        """CUDA graph of one device-resident step over fixed buffers (see CapturedStep)."""
+        return CapturedStep(self, batch, testing, out, warmup)
+
     #: raw bytes above which fit_host streams the blocks in chunks (copy of chunk c+1 overlaps the
     #: scatter + partial Gram of chunk c); below it one copy + one launch of each kernel is faster
     pipeline_min_bytes = 64 << 20
@@ -132,3 +136,34 @@ class LinearFitPipeline:
         summary = SimpleNamespace(ncfg=ncfg, k=k, row_begin=0, row_end=n_out, n_rows_out=n_out, h2d_bytes=int(h2d),
                                   chunks=len(batches))
         return x, res, summary
+
+
+class CapturedStep:
+    """One device-resident step (scatter -> Gram -> [all-reduce] -> factor/solve -> refinement) captured into a
+    CUDA graph: the ~11 launches of a narrow fit (k ~ 100; many more for blocked factorisations) become one
+    `cudaGraphLaunch`, which is what a caller re-fitting the same buffers wants (hyper-parameter scans over
+    group weights: rewrite `batch.eweight/fweight/vweight` in place, replay).  The buffers of `batch`, `testing`
+    and `out` are baked into the graph by address; results land in the same `FitResult` tensors on every replay.
+    All launches go through the C-ABI on the capturing stream; the library allocates nothing and never
+    synchronises, so the path is capturable as is."""
+
+    def __init__(self, pipe: LinearFitPipeline, batch: ConfigBatch, testing=None, out=None, warmup=2):
+        self.pipe, self.batch = pipe, batch
+        dev = pipe.engine.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):            # warm-up: workspaces, function attributes, NCCL channels
+            for _ in range(max(1, int(warmup))):
+                res = pipe.fit_batch(batch, testing, out)
+            if out is None:                       # keep the outputs of the scatter at a fixed address
+                out = (res.extra["A"], res.extra["b"], res.extra["w"])
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = pipe.fit_batch(batch, testing, out)
+        self.launches = self.result.launches + 1      # kernels inside one replay (scatter + the fit)
+
+    def replay(self) -> FitResult:
+        self.graph.replay()
+        return self.result

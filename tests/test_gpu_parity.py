@@ -499,3 +499,21 @@ def test_group_stats_and_ta_metrics_golden(engine, ta):
             for m in ("mae", "rmse", "rsq"):
                 assert np.isclose(row[m], ref[pre + m], rtol=1e-9, atol=1e-13), (key, wname, m, row[m], ref[pre + m])
             assert row["ncount"] == ref[pre + "ncount"]
+
+
+def test_captured_step_replays_the_eager_step(engine):
+    """CUDA-graph replay == eager step bit for bit, and it follows in-place edits of the inputs."""
+    from fitsnap_b200.pipeline import LinearFitPipeline
+    g = load_golden("scatter_snap_b0_efs.npz")
+    pipe = LinearFitPipeline(int(g["numtypes"]), int(g["ncoeff"]), bool(int(g["bzeroflag"])), g["blank2j"], alpha=1e-8,
+                             refine=2, engine=engine, energy=bool(int(g["use_energy"])),
+                             force=bool(int(g["use_force"])), stress=bool(int(g["use_stress"])))
+    batch = pipe.pack(g["raw"], g["natoms"], g["volume"], g["energy"], g["forces"], g["stress"], g["eweight"],
+                      g["fweight"], g["vweight"], g["type_fraction"])
+    eager = pipe.fit_batch(batch).x.clone()
+    cap = pipe.capture(batch)
+    assert torch.equal(cap.replay().x, eager)
+    batch.fweight.mul_(3.0)                      # edit the inputs in place: the replay must see it
+    x2 = cap.replay().x.clone()
+    assert torch.equal(x2, pipe.fit_batch(batch).x)
+    assert not torch.equal(x2, eager)
