@@ -23,7 +23,10 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = Engine(local)
     ok = True
-    for case, alpha in (("well", 0.0), ("ill", 0.0), ("wide", 1e-6), ("zerocol", 0.0)):
+    cases = [("well", 0.0, "auto"), ("ill", 0.0, "auto"), ("wide", 1e-6, "auto"), ("zerocol", 0.0, "auto"),
+             ("ill", 0.0, "int8"), ("wide", 1e-6, "int8")]     # int8: the tcgen05 exact-integer Gram per shard
+    for case, alpha, path in cases:
+        eng.set_gram_path(path)
         a, b, w, t = synth_system(**SOLVE_CASES[case])
         lo, hi = shard_rows(a.shape[0], world, rank)
         A, B, W = eng.to_device(a[lo:hi]), eng.to_device(b[lo:hi]), eng.to_device(w[lo:hi])
@@ -38,8 +41,8 @@ def main():
             mr, l2, _ = lf.coeff_rel_err(x.cpu().numpy(), ref)
             good = same and mr < 1e-10
             ok = ok and good
-            print("dist_parity world=%d case=%s alpha=%g: max_rel=%.2e l2=%.2e identical_on_all_ranks=%s %s"
-                  % (world, case, alpha, mr, l2, same, "OK" if good else "FAIL"), flush=True)
+            print("dist_parity world=%d case=%s alpha=%g gram=%s: max_rel=%.2e l2=%.2e identical_on_all_ranks=%s %s"
+                  % (world, case, alpha, path, mr, l2, same, "OK" if good else "FAIL"), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
