@@ -2,7 +2,7 @@
 
     import fitsnap_b200.plugin as plugin
     plugin.register()                      # before FitSnap(...) is constructed
-    fs = FitSnap(infile_or_dict, comm)     # [SOLVER] solver = SVD | RIDGE, [CALCULATOR] calculator = LAMMPSSNAP | LAMMPSPACE
+    fs = FitSnap(infile_or_dict, comm)     # [SOLVER] solver = SVD | RIDGE | LASSO | ANL, [CALCULATOR] calculator = LAMMPSSNAP | LAMMPSPACE
 
 How discovery works in the reference (and why this is all that is needed):
   * solvers/solver_factory.py:25-34 walks `Solver.__subclasses__()` comparing lower-cased class
@@ -59,6 +59,8 @@ def register(engine=None):
     _registered["RIDGE"] = solver_class("RIDGE", bs.RIDGE)
     if hasattr(bs, "LASSO"):
         _registered["LASSO"] = solver_class("LASSO", bs.LASSO)
+    if hasattr(bs, "ANL"):
+        _registered["ANL"] = solver_class("ANL", bs.ANL)
     _registered["LammpsSnap"] = calculator_class("LammpsSnap", bc.SnapCollectMixin, RefSnap)
     _registered["LammpsPace"] = calculator_class("LammpsPace", bc.PaceCollectMixin, RefPace)
     return dict(_registered)

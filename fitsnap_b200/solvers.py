@@ -5,6 +5,7 @@ same result convention as the reference:
     fitsnap3lib/solvers/svd.py:13-54     class SVD(Solver).perform_fit(a, b, w, fs_dict, trainall)
     fitsnap3lib/solvers/ridge.py:6-60    class RIDGE(Solver).perform_fit(...)   [RIDGE] alpha, local_solver
     fitsnap3lib/solvers/lasso.py:9-30    class LASSO(Solver).perform_fit()      [LASSO] alpha, max_iter
+    fitsnap3lib/solvers/anl.py:7-67      class ANL(Solver).perform_fit(a, b, w, trainall)  [SOLVER] cov_nugget, nsam
     fitsnap3lib/solvers/solver.py:19-46  Solver.__init__(name, pt, config, linear=True), fit_gather()
 
 The classes here do NOT import fitsnap3lib (it is absent on a bare GPU box); they duck-type
@@ -271,3 +272,59 @@ class LASSO(LinearSolverBase):
         x, info = eng.lasso(gaug, n_train, alpha, max_iter, self.tol)
         self.info = {"not_converged": int(info[0].item()), "sweeps": int(info[1].item())}
         self.fit = x.detach().cpu().numpy().astype(np.float64, copy=True)
+
+
+class ANL(LinearSolverBase):
+    """Drop-in for fitsnap3lib.solvers.anl.ANL (analytical Bayesian linear regression, anl.py:13-67):
+        mean = pinv(aw^T aw + nugget I) aw^T bw,   cov = sigmahat * pinv(...),
+        sigmahat = (|bw - aw mean|^2 / 2) / ((n_train - k)/2 - 1),   fit_sam ~ N(mean, cov) x nsam,
+    with nugget = [SOLVER] cov_nugget and nsam = [SOLVER] nsam; like the reference it drops `covariance.npy`
+    and `mean.npy` into the working directory (anl.py:60-61).
+    Device side: the Gram pass, the mean (Cholesky of G + nugget I refined against A, or the minimum-norm
+    path when nugget = 0 meets dependent columns -- pinv semantics) and |res|^2 (one pass, `fsb_group_stats`).
+    The k x k symmetrised pseudo-inverse that scales into the covariance is post-processing of the reduced
+    problem and is done with numpy on the all-reduced Gram, exactly as anl.py:41-44 states it."""
+
+    #: write covariance.npy / mean.npy like the reference (tests switch it off)
+    save_files = True
+
+    def __init__(self, name, pt, config):
+        super().__init__(name, pt, config)
+        self.cov = None
+        self.fit_sam = None
+
+    def _alpha(self):
+        return float(_get(_section(self.config, "SOLVER"), "cov_nugget", 0.0))
+
+    def perform_fit(self, a=None, b=None, w=None, trainall=False, fs_dict=None):
+        pt = self.pt
+        sharded = self.process_group is not None
+        if getattr(pt, "_rank", 0) != 0 and not sharded:      # anl.py:14 sub_rank_zero
+            return
+        super().perform_fit(a, b, w, fs_dict, trainall)       # mean -> self.fit
+        res = self.last_result
+        a, b, w, testing = self._resolve_inputs(a, b, w, fs_dict, trainall)
+        A, B, W, T = self._to_device(a, b, w, testing)
+        eng = self._engine()
+        # |bw - aw mean|^2 and the training row count from one pass: group 0 = training, 1 = test rows
+        gid = torch.zeros(A.shape[0], dtype=torch.int32, device=eng.device) if T is None else T.to(torch.int32)
+        x = eng.to_device(np.asarray(self.fit, dtype=np.float64))
+        stats = eng.group_stats(A, B, W, gid, x, 2)
+        if sharded:
+            import torch.distributed as dist
+            dist.all_reduce(stats, group=self.process_group)
+        stats = stats.cpu().numpy()
+        npt, wsq = float(stats[0, 0]), float(stats[0, 7])
+        k = A.shape[1]
+        nugget = self._alpha()
+        g = res.gaug[:k, :k].cpu().numpy()
+        invptp = np.linalg.pinv(g + nugget * np.diag(np.ones((k,))))      # anl.py:41
+        invptp = invptp * 0.5 + invptp.T * 0.5                            # anl.py:42
+        sigmahat = (wsq / 2.0) / ((npt - k) / 2.0 - 1.0)                  # anl.py:48-52
+        self.cov = sigmahat * invptp                                      # anl.py:56
+        if self.save_files and getattr(pt, "_rank", 0) == 0:
+            np.save("covariance.npy", self.cov)
+            np.save("mean.npy", self.fit)
+        nsam = int(_get(_section(self.config, "SOLVER"), "nsam", 0))
+        if nsam:
+            self.fit_sam = np.random.multivariate_normal(self.fit, self.cov, size=(nsam,))   # anl.py:65

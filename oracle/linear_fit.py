@@ -167,6 +167,21 @@ def ridge_fit_exact(a, b, w, alpha, testing=None):
     return lstsq(aug, rhs)[0]
 
 
+def anl_fit(a, b, w, cov_nugget=0.0, testing=None):
+    """anl.py:19-58 `ANL.perform_fit`: posterior mean pinv(aw^T aw + nugget I) aw^T bw (symmetrised
+    inverse, anl.py:41-44), data-noise estimate sigmahat = (|res|^2 / 2) / ((npt - nbas)/2 - 1)
+    (anl.py:48-52) and the posterior covariance sigmahat * inverse (anl.py:56).  Returns (mean, cov)."""
+    aw, bw = weighted_system(a, b, w, testing)
+    npt, nbas = aw.shape
+    invptp = np.linalg.pinv(aw.T @ aw + cov_nugget * np.diag(np.ones((nbas,))))
+    invptp = invptp * 0.5 + invptp.T * 0.5
+    mean = invptp @ (aw.T @ bw)
+    res = bw - aw @ mean
+    bp = (res @ res) / 2.0
+    ap = (npt - nbas) / 2.0
+    return mean, (bp / (ap - 1.0)) * invptp
+
+
 def lasso_fit(a, b, w, alpha, max_iter, testing=None, apply_transpose=False, tol=1e-4):
     """lasso.py:15-30 `LASSO.perform_fit`: sklearn Lasso(alpha, fit_intercept=False,
     max_iter) = argmin 1/(2 n) |bw - aw x|^2 + alpha |x|_1 (coordinate descent)."""

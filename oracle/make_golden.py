@@ -69,6 +69,17 @@ def solve_cases():
         print("solve_%s" % name, a.shape)
 
 
+def anl_cases():
+    """Posterior mean + covariance of the reference's ANL solver (anl.py) on two seeded systems."""
+    for name, nugget in (("well", 0.0), ("zerocol", 1e-8)):
+        a, b, w, testing = synth_system(**SOLVE_CASES[name])
+        mean, cov = rd.ref_anl(a, b, w, testing=testing, cov_nugget=nugget)
+        np.savez_compressed(os.path.join(OUT, "anl_%s.npz" % name), ref_mean=mean, ref_cov=cov,
+                            cov_nugget=np.float64(nugget),
+                            checksum=np.array([a.sum(), b.sum(), w.sum(), testing.sum()]))
+        print("anl_%s" % name, cov.shape)
+
+
 def scatter_cases():
     rng = np.random.default_rng(77)
     combos = [
@@ -147,6 +158,7 @@ def main():
     assert rd.reference_available(), "needs the reference tree at %s" % rd.REFERENCE_ROOT
     ta_linear()
     solve_cases()
+    anl_cases()
     scatter_cases()
 
 

@@ -148,6 +148,8 @@ def reference_solver(name, pt, cfg):
         from fitsnap3lib.solvers.ridge import RIDGE as cls
     elif name.upper() == "LASSO":
         from fitsnap3lib.solvers.lasso import LASSO as cls
+    elif name.upper() == "ANL":
+        from fitsnap3lib.solvers.anl import ANL as cls
     else:
         raise KeyError(name)
     return cls(name, pt, cfg)
@@ -174,6 +176,31 @@ def ref_fit(name, a, b, w, testing=None, **ctx):
     else:
         s.perform_fit(a=a, b=b, w=w, trainall=True)
     return np.array(s.fit, dtype=np.float64), s
+
+
+def ref_anl(a, b, w, testing=None, cov_nugget=0.0, nsam=0):
+    """Run the reference ANL.perform_fit (anl.py:13-67) in a scratch directory (it drops covariance.npy and
+    mean.npy into the working directory, anl.py:60-61).  Returns (mean, cov)."""
+    import tempfile
+    pt, cfg = make_reference_context(solver="ANL", extra={"SOLVER": {"cov_nugget": cov_nugget, "nsam": nsam}})
+    s = reference_solver("ANL", pt, cfg)
+    # the explicit-array branch (anl.py:28) forgets to mask `w`, like svd.py:46: go through pt.shared_arrays
+    n, k = a.shape
+    pt.create_shared_array("a", n, k)
+    pt.create_shared_array("b", n)
+    pt.create_shared_array("w", n)
+    pt.shared_arrays["a"].array[:] = a.reshape(pt.shared_arrays["a"].array.shape)
+    pt.shared_arrays["b"].array[:] = b
+    pt.shared_arrays["w"].array[:] = w
+    pt.fitsnap_dict["Testing"] = [bool(t) for t in testing] if testing is not None else [False] * n
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            s.perform_fit()
+        finally:
+            os.chdir(cwd)
+    return np.array(s.fit, dtype=np.float64), np.array(s.cov, dtype=np.float64)
 
 
 def make_config_dict(natoms, numtypes, rng, type_names, group="G", fname="cfg", eweight=1.0,

@@ -517,3 +517,24 @@ def test_captured_step_replays_the_eager_step(engine):
     x2 = cap.replay().x.clone()
     assert torch.equal(x2, pipe.fit_batch(batch).x)
     assert not torch.equal(x2, eager)
+
+
+@pytest.mark.parametrize("name", ["well", "zerocol"])
+def test_anl_dropin_matches_reference_fixture(engine, name, tmp_path, monkeypatch):
+    """ANL drop-in (solvers.py) on the device path vs the reference's posterior mean and covariance."""
+    from types import SimpleNamespace
+    from fitsnap_b200.solvers import ANL
+    g = load_golden("anl_%s.npz" % name)
+    a, b, w, t = synth_system(**SOLVE_CASES[name])
+    pt = SimpleNamespace(_rank=0, shared_arrays={}, fitsnap_dict={"Testing": [bool(v) for v in t]})
+    cfg = SimpleNamespace(sections={"SOLVER": SimpleNamespace(cov_nugget=float(g["cov_nugget"]), nsam=3)})
+    s = ANL("ANL", pt, cfg)
+    s.engine = engine
+    monkeypatch.chdir(tmp_path)
+    s.perform_fit(a=a, b=b, w=w)
+    mr, l2, _ = lf.coeff_rel_err(s.fit, g["ref_mean"])
+    assert mr < 1e-8, (mr, l2)       # the reference's own pinv-of-Gram mean is only ~cond^2 eps accurate
+    assert np.max(np.abs(s.cov - g["ref_cov"])) < 1e-7 * np.max(np.abs(g["ref_cov"]))
+    assert s.fit_sam.shape == (3, a.shape[1])
+    assert np.array_equal(np.load(tmp_path / "mean.npy"), s.fit)
+    assert np.load(tmp_path / "covariance.npy").shape == s.cov.shape

@@ -83,3 +83,15 @@ def test_oracle_against_live_reference():
     assert np.array_equal(rd.ref_fit("RIDGE", a, b, w, testing=t, ridge_alpha=1e-4)[0], lf.ridge_fit(a, b, w, 1e-4, t))
     x_t = rd.ref_fit("SVD", a, b, w, apply_transpose=1)[0]
     assert np.array_equal(x_t, lf.svd_fit(a, b, w, apply_transpose=True))
+
+
+@pytest.mark.parametrize("name", ["well", "zerocol"])
+def test_oracle_anl_matches_reference_fixture(name):
+    """oracle.linear_fit.anl_fit restates anl.py:19-58; fixture written by the unmodified reference."""
+    from tests.synth import SOLVE_CASES, synth_system
+    g = load_golden("anl_%s.npz" % name)
+    a, b, w, t = synth_system(**SOLVE_CASES[name])
+    assert np.allclose([a.sum(), b.sum(), w.sum(), t.sum()], g["checksum"], rtol=1e-13)
+    mean, cov = lf.anl_fit(a, b, w, float(g["cov_nugget"]), t)
+    assert np.max(np.abs(mean - g["ref_mean"])) <= 1e-9 * np.max(np.abs(g["ref_mean"]))
+    assert np.max(np.abs(cov - g["ref_cov"])) <= 1e-8 * np.max(np.abs(g["ref_cov"]))

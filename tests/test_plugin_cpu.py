@@ -109,3 +109,22 @@ def test_device_error_analysis_matches_reference_table(registered):
         r, d = ref[col].values.astype(float), dev[col].values.astype(float)
         ok = np.isclose(d, r, rtol=1e-9, atol=1e-12) | (np.isnan(d) & np.isnan(r)) | (~np.isfinite(r) & ~np.isfinite(d))
         assert ok.all(), (col, ref[col][~ok], dev[col][~ok])
+
+
+def test_dropin_anl_matches_reference_mean_and_covariance(registered):
+    """[SOLVER] solver = ANL resolves to the drop-in; posterior mean / covariance / samples follow anl.py:40-65
+    (host logic on the test double here, the kernels on the GPU in tests/test_gpu_parity.py)."""
+    from fitsnap3lib.solvers.solver_factory import solver
+    from tests.synth import SOLVE_CASES, synth_system
+    a, b, w, t = synth_system(**SOLVE_CASES["well"])
+    mean_ref, cov_ref = rd.ref_anl(a, b, w, testing=t, cov_nugget=1e-8)
+    pt, cfg = rd.make_reference_context(solver="ANL", extra={"SOLVER": {"cov_nugget": 1e-8, "nsam": 5}})
+    s = solver("ANL", pt, cfg)
+    assert type(s) is registered["ANL"]
+    s.save_files = False
+    s.refine = 2
+    pt.fitsnap_dict["Testing"] = [bool(v) for v in t]
+    s.perform_fit(a=a, b=b, w=w)
+    assert np.max(np.abs(s.fit - mean_ref)) < 1e-9 * np.max(np.abs(mean_ref))
+    assert np.max(np.abs(s.cov - cov_ref)) < 1e-7 * np.max(np.abs(cov_ref))
+    assert s.fit_sam.shape == (5, a.shape[1])
