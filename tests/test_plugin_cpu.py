@@ -128,3 +128,37 @@ def test_dropin_anl_matches_reference_mean_and_covariance(registered):
     assert np.max(np.abs(s.fit - mean_ref)) < 1e-9 * np.max(np.abs(mean_ref))
     assert np.max(np.abs(s.cov - cov_ref)) < 1e-7 * np.max(np.abs(cov_ref))
     assert s.fit_sam.shape == (5, a.shape[1])
+
+
+def test_coefficient_file_round_trip(registered):
+    """drop-in fit -> reference `_offset` (solver.py:78-102, bzeroflag = 1) -> reference
+    `.snapcoeff` text (io/outputs/snap.py:157-188, 18 significant digits) -> parsed back as read_fit does
+    (snap.py:90-121): the coefficients survive to the last bit the format keeps."""
+    from fitsnap3lib.solvers.solver_factory import solver
+    from fitsnap3lib.io.outputs.snap import _to_coeff_string
+    rng = np.random.default_rng(21)
+    kw = dict(numtypes=2, types="In P", twojmax="4 4", bzeroflag=1)
+    pt0, cfg0 = rd.make_reference_context(**kw)
+    nc = cfg0.sections["BISPECTRUM"].ncoeff
+    cfgs, blocks, vols = _configs(rng, nc, 2, n_cfg=60)
+    a, b, w, lists, cfg, pt, calc = rd.ref_scatter(cfgs, blocks, vols, use_factory=True, **kw)
+    s = solver("SVD", pt, cfg)
+    s.refine = 2
+    s.perform_fit()
+    raw_fit = s.fit.copy()
+    s.error_analysis()                       # applies _offset: one leading 0 per type when bzeroflag = 1
+    fit = np.asarray(s.fit, dtype=np.float64).reshape(-1)
+    assert fit.shape[0] == 2 * (nc + 1) and fit[0] == 0.0 and fit[nc + 1] == 0.0
+    assert np.array_equal(np.delete(fit, [0, nc + 1]), raw_fit)
+    text = _to_coeff_string(cfg, fit)
+    lines = text.splitlines()
+    ntypes, ncoeff1 = (int(v) for v in lines[2].split())
+    assert (ntypes, ncoeff1) == (2, nc + 1)
+    parsed, pos = [], 3
+    for _ in range(ntypes):
+        pos += 1                             # element header
+        for _j in range(ncoeff1):
+            parsed.append(float(lines[pos].split()[0]))
+            pos += 1
+    parsed = np.array(parsed)
+    assert np.max(np.abs(parsed - fit)) <= 1e-17 * np.max(np.abs(fit)) + 1e-300
