@@ -601,7 +601,10 @@ __global__ void __launch_bounds__(256, 3) scatter_kernel(ScatterArgs p, int64_t 
         bv = (p.energy[c] - ref) / (double)n;             // lammps_snap.py:473
         wv = p.eweight[c];
       } else if (kind == 1) {
-        const int64_t atom0 = (p.raw_row_off[c] - p.raw_row_off[0] - 7 * (int64_t)c) / 3;
+        // atoms before configuration c = (raw rows before it - 7 c) / 3: an exact multiple of 3, so the
+        // quotient is one multiply by the inverse of 3 modulo 2^64 (a 64-bit division costs ~100 instructions)
+        const int64_t atom0 = (int64_t)((uint64_t)(p.raw_row_off[c] - p.raw_row_off[0] - 7 * (int64_t)c) *
+                                        0xAAAAAAAAAAAAAAABull);
         bv = p.forces[3 * atom0 + sub] - ref;             // :506-507
         wv = p.fweight[c];
       } else {

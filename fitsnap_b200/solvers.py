@@ -276,14 +276,15 @@ class LASSO(LinearSolverBase):
 
 class ANL(LinearSolverBase):
     """Drop-in for fitsnap3lib.solvers.anl.ANL (analytical Bayesian linear regression, anl.py:13-67):
-        mean = pinv(aw^T aw + nugget I) aw^T bw,   cov = sigmahat * pinv(...),
+        invptp = sym(pinv(aw^T aw + nugget I)),   mean = invptp aw^T bw,   cov = sigmahat * invptp,
         sigmahat = (|bw - aw mean|^2 / 2) / ((n_train - k)/2 - 1),   fit_sam ~ N(mean, cov) x nsam,
     with nugget = [SOLVER] cov_nugget and nsam = [SOLVER] nsam; like the reference it drops `covariance.npy`
     and `mean.npy` into the working directory (anl.py:60-61).
-    Device side: the Gram pass, the mean (Cholesky of G + nugget I refined against A, or the minimum-norm
-    path when nugget = 0 meets dependent columns -- pinv semantics) and |res|^2 (one pass, `fsb_group_stats`).
-    The k x k symmetrised pseudo-inverse that scales into the covariance is post-processing of the reduced
-    problem and is done with numpy on the all-reduced Gram, exactly as anl.py:41-44 states it."""
+    Device side: the two passes over A -- the fused mask/weight/Gram pass (`fsb_gram`) and |res|^2 with the
+    training row count (`fsb_group_stats`).  Everything between them is k x k algebra on the all-reduced Gram and
+    is kept as anl.py:41-44 states it (numpy `pinv`, default rcond 1e-15 ON THE EIGENVALUES of the Gram, i.e. a
+    rank truncation at sigma/sigma_max ~ 3e-8 -- replacing it by the refined Cholesky solve of the SVD/RIDGE
+    drop-ins would change the answer whenever that truncation bites)."""
 
     #: write covariance.npy / mean.npy like the reference (tests switch it off)
     save_files = True
@@ -301,27 +302,28 @@ class ANL(LinearSolverBase):
         sharded = self.process_group is not None
         if getattr(pt, "_rank", 0) != 0 and not sharded:      # anl.py:14 sub_rank_zero
             return
-        super().perform_fit(a, b, w, fs_dict, trainall)       # mean -> self.fit
-        res = self.last_result
         a, b, w, testing = self._resolve_inputs(a, b, w, fs_dict, trainall)
         A, B, W, T = self._to_device(a, b, w, testing)
         eng = self._engine()
-        # |bw - aw mean|^2 and the training row count from one pass: group 0 = training, 1 = test rows
-        gid = torch.zeros(A.shape[0], dtype=torch.int32, device=eng.device) if T is None else T.to(torch.int32)
-        x = eng.to_device(np.asarray(self.fit, dtype=np.float64))
-        stats = eng.group_stats(A, B, W, gid, x, 2)
+        gaug = eng.gram(A, B, W, T)
         if sharded:
             import torch.distributed as dist
+            dist.all_reduce(gaug, group=self.process_group)
+        k = A.shape[1]
+        gh = gaug.cpu().numpy()
+        nugget = self._alpha()
+        invptp = np.linalg.pinv(gh[:k, :k] + nugget * np.diag(np.ones((k,))))     # anl.py:41
+        invptp = invptp * 0.5 + invptp.T * 0.5                                   # anl.py:42
+        self.fit = np.dot(invptp, gh[:k, k])                                     # anl.py:44
+        # |bw - aw mean|^2 and the training row count from one pass: group 0 = training, 1 = test rows
+        gid = torch.zeros(A.shape[0], dtype=torch.int32, device=eng.device) if T is None else T.to(torch.int32)
+        stats = eng.group_stats(A, B, W, gid, eng.to_device(self.fit), 2)
+        if sharded:
             dist.all_reduce(stats, group=self.process_group)
         stats = stats.cpu().numpy()
         npt, wsq = float(stats[0, 0]), float(stats[0, 7])
-        k = A.shape[1]
-        nugget = self._alpha()
-        g = res.gaug[:k, :k].cpu().numpy()
-        invptp = np.linalg.pinv(g + nugget * np.diag(np.ones((k,))))      # anl.py:41
-        invptp = invptp * 0.5 + invptp.T * 0.5                            # anl.py:42
-        sigmahat = (wsq / 2.0) / ((npt - k) / 2.0 - 1.0)                  # anl.py:48-52
-        self.cov = sigmahat * invptp                                      # anl.py:56
+        sigmahat = (wsq / 2.0) / ((npt - k) / 2.0 - 1.0)                         # anl.py:48-52
+        self.cov = sigmahat * invptp                                             # anl.py:56
         if self.save_files and getattr(pt, "_rank", 0) == 0:
             np.save("covariance.npy", self.cov)
             np.save("mean.npy", self.fit)
