@@ -9,6 +9,7 @@
 #include "fsb_common.cuh"
 #include <float.h>
 #include <stdlib.h>
+#include <limits.h>
 
 namespace {
 
@@ -689,6 +690,230 @@ __global__ void __launch_bounds__(256, 3) scatter_kernel(ScatterArgs p, int64_t 
   if (p.nonfinite && __any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(p.nonfinite, 1);
 }
 
+
+// ------------------------------------------------------------------------------ K1, bulk-copy staged
+// Fast path of the scatter for the common layout: energy + force + virial rows all assembled (output row i
+// comes from raw row i), narrow rows (k <= 160), contiguous A (lda == k), row -> configuration map given.
+// scatter_kernel above issues ~56 instructions per matrix element (address arithmetic, predicates, per-kind
+// branches around global loads and stores) and is half issue-bound, half latency-bound (4.8 TB/s).  Here the
+// global traffic is moved by the TMA unit: one producer thread streams tiles of SB_ROWS raw rows (contiguous)
+// into a shared-memory ring (cp.async.bulk, mbarrier complete_tx), 8 consumer warps transform them from shared
+// memory into a shared-memory output tile (same operations in the same order as scatter_kernel: bit-identical
+// A, b, w), and one thread writes the tile back with cp.async.bulk.global.shared::cta (bulk_group).  Row
+// metadata (configuration, row family, divisor, truth, weight) of the NEXT tile is prefetched into registers.
+// Tiles that cannot be bulk-copied (the ragged last tile, 16-byte misalignment) are moved with plain loads
+// and stores by the consumers; the arithmetic is shared.
+constexpr int SB_ROWS = 32;
+constexpr int SB_CONSUMERS = 256;
+constexpr int SB_META = 6;                              // metadata warps (one per ring slot, <= nstage active)
+constexpr int SB_THREADS = SB_CONSUMERS + 32 + 32 * SB_META;
+constexpr int SB_RPW = SB_ROWS / (SB_CONSUMERS / 32);   // 4 rows of a tile per consumer warp
+constexpr int SB_MAXK = 160;
+constexpr int SB_NCH = SB_MAXK / 32;                    // column chunks of 32 held in registers per lane
+
+struct SbRowMeta {      // one per row of a tile, written by the producer warp
+  double div, wv, truth;
+  int cfg, kind;        // kind: 0 energy, 1 force, 2 virial, -1 past the end
+};
+
+__global__ void __launch_bounds__(SB_THREADS, 1) scatter_bulk_kernel(ScatterArgs p, int64_t total,
+                                                                     int64_t tiles_per_cta, int nstage) {
+  extern __shared__ __align__(128) unsigned char sb_raw[];
+  __shared__ __align__(8) unsigned long long s_full[8];
+  __shared__ __align__(8) unsigned long long s_empty[8];
+  __shared__ SbRowMeta s_meta[8][SB_ROWS];
+  const bool bzero = p.flags & FSB_BZEROFLAG;
+  const bool do_scrub = p.flags & FSB_SCRUB_NONFINITE;
+  const int kraw = p.ncoeff * p.numtypes;
+  const int k = bzero ? kraw : kraw + p.numtypes;
+  const int seg = p.ncoeff + 1;
+  const int ldr = kraw + 1;
+  const size_t raw_doubles = (size_t)SB_ROWS * ldr;
+  double* ring = reinterpret_cast<double*>(sb_raw);                 // nstage raw tiles
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  const int64_t ntiles = (total + SB_ROWS - 1) / SB_ROWS;
+  const int64_t t_begin = (int64_t)blockIdx.x * tiles_per_cta;
+  int64_t t_end = t_begin + tiles_per_cta;
+  if (t_end > ntiles) t_end = ntiles;
+  const int64_t row0 = p.out_row_off[0];
+  const int64_t rraw0 = p.raw_row_off[0];
+  // a tile goes through the TMA unit when it is full and its source is 16-byte aligned
+  auto tile_is_bulk = [&](int64_t t) {
+    const int64_t i0 = t * SB_ROWS;
+    const bool full = (total - i0) >= SB_ROWS;
+    const uintptr_t src = reinterpret_cast<uintptr_t>(p.raw + (rraw0 + i0) * ldr);
+    return full && (src & 15) == 0;
+  };
+
+  if (tid == 0) {
+    for (int i = 0; i < nstage; ++i) {
+      // full: the expect_tx arrival of the bulk copy (or a plain arrival) + the arrival after the metadata
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bk_smem_u32(&s_full[i])), "r"(2) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bk_smem_u32(&s_empty[i])), "r"(SB_CONSUMERS / 32)
+                   : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == SB_CONSUMERS / 32) {
+    // ---- copy producer: one thread streams the raw tiles (non-bulk tiles are filled by the consumers; the slot /
+    //      phase bookkeeping stays in step)
+    if (lane == 0) {
+      for (int64_t t = t_begin; t < t_end; ++t) {
+        const int it = (int)(t - t_begin);
+        const int slot = it % nstage, n = it / nstage;
+        if (it >= nstage) bk_mbar_wait(bk_smem_u32(&s_empty[slot]), (unsigned)((n - 1) & 1));
+        const unsigned full = bk_smem_u32(&s_full[slot]);
+        if (tile_is_bulk(t)) {
+          const unsigned bytes = (unsigned)(raw_doubles * sizeof(double));
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(bk_smem_u32(ring + slot * raw_doubles)), "l"(p.raw + (rraw0 + t * SB_ROWS) * ldr),
+                         "r"(bytes), "r"(full) : "memory");
+        } else {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");   // slot handed over empty
+        }
+      }
+    }
+    return;
+  }
+  if (warp > SB_CONSUMERS / 32) {
+    // ---- metadata producers: one warp per ring slot, lane r resolves row r of the tile.  Resolving a
+    //      row is a chain of dependent global loads (row -> configuration -> offsets -> truth, ~2 us): done here,
+    //      several tiles in flight, it never stalls the consumers.  Published in shared memory with the second
+    //      arrival on the tile's barrier.
+    const int mw = warp - SB_CONSUMERS / 32 - 1;
+    const int64_t n_force = total - 7 * (int64_t)p.ncfg > 1 ? total - 7 * (int64_t)p.ncfg : 1;   // 3 * atoms
+    // warp m owns ring slot m: the tiles of one slot are then resolved strictly in order, which the parity-based
+    // mbarrier wait needs (a waiter two phases ahead of the barrier would see a matching parity and run early)
+    for (int64_t t = t_begin + mw; mw < nstage && t < t_end; t += nstage) {
+      const int it = (int)(t - t_begin);
+      const int slot = it % nstage, n = it / nstage;
+      if (it >= nstage) bk_mbar_wait(bk_smem_u32(&s_empty[slot]), (unsigned)((n - 1) & 1));
+      SbRowMeta m;
+      m.cfg = 0; m.kind = -1; m.div = 1.0; m.wv = 0.0; m.truth = 0.0;
+      const int64_t i = t * SB_ROWS + lane;
+      if (i < total) {
+        // two levels of loads instead of four: everything that depends only on the configuration index is
+        // requested at once (rows map 1:1, so the force component of row i is forces[i - 7 c - 1] whatever
+        // the row family turns out to be; the index is clamped for the rows that will not use it)
+        const int c = __ldg(p.row_cfg + i);
+        int64_t fi = i - 7 * (int64_t)c - 1;
+        fi = fi < 0 ? 0 : (fi > n_force - 1 ? n_force - 1 : fi);
+        const int nat = __ldg(p.natoms + c);
+        const int64_t off_c = __ldg(p.out_row_off + c);
+        const double ew = __ldg(p.eweight + c), fw = __ldg(p.fweight + c), vw = __ldg(p.vweight + c);
+        const double en = __ldg(p.energy + c), vol = __ldg(p.volume + c), fo = __ldg(p.forces + fi);
+        const int64_t local = row0 + i - off_c;
+        m.cfg = c;
+        if (local == 0) {
+          m.kind = 0; m.div = (double)nat; m.wv = ew; m.truth = en;
+        } else if (local < 1 + 3 * (int64_t)nat) {
+          m.kind = 1; m.wv = fw; m.truth = fo;
+        } else {
+          const int sub = (int)(local - 1 - 3 * (int64_t)nat);
+          const int vi[6] = {0, 1, 2, 1, 0, 0}, vj[6] = {0, 1, 2, 2, 2, 1};
+          m.kind = 2; m.div = vol; m.wv = vw;
+          m.truth = __ldg(p.stress + (size_t)c * 9 + vi[sub] * 3 + vj[sub]);
+        }
+      }
+      s_meta[slot][lane] = m;
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bk_smem_u32(&s_full[slot])) : "memory");
+    }
+    return;
+  }
+
+  // ---- consumers: the column map of this lane is loop-invariant, kept in registers
+  bool bad = false;
+  int srcc[SB_NCH];       // >= 0: raw column; < 0: lead column of type (-v-1); INT_MIN: column past k
+  double pref[SB_NCH];
+#pragma unroll
+  for (int u = 0; u < SB_NCH; ++u) {
+    const int oc = lane + 32 * u;
+    srcc[u] = INT_MIN;
+    pref[u] = 0.0;
+    if (oc < k) {
+      int v = oc;
+      if (!bzero) {
+        const int t = oc / seg, q = oc - t * seg;
+        v = (q == 0) ? -(t + 1) : t * p.ncoeff + q - 1;
+      }
+      srcc[u] = v;
+      pref[u] = __ldg(p.blank2j + oc);
+    }
+  }
+  for (int64_t t = t_begin; t < t_end; ++t) {
+    const int it = (int)(t - t_begin);
+    const int slot = it % nstage, n = it / nstage;
+    const int64_t i0 = t * SB_ROWS;
+    const int nr = (int)((total - i0) < SB_ROWS ? (total - i0) : SB_ROWS);
+    const bool bulk = tile_is_bulk(t);
+    double* rin = ring + slot * raw_doubles;
+    bk_mbar_wait(bk_smem_u32(&s_full[slot]), (unsigned)(n & 1));
+    if (!bulk) {   // plain loads into the slot (ragged last tile / misaligned views)
+      const double* src = p.raw + (rraw0 + i0) * ldr;
+      for (int e = tid; e < nr * ldr; e += SB_CONSUMERS) rin[e] = __ldg(src + e);
+    }
+    if (!bulk) asm volatile("bar.sync 1, %0;" ::"n"(SB_CONSUMERS) : "memory");   // block-uniform
+
+#pragma unroll
+    for (int q = 0; q < SB_RPW; ++q) {
+      const int lr = warp * SB_RPW + q;
+      const SbRowMeta m = s_meta[slot][lr];                     // broadcast read
+      if (m.kind < 0) continue;                                 // past the end (warp-uniform)
+      const double* rrow = rin + (size_t)lr * ldr;
+      double* orow = p.A + (row0 + i0 + lr) * (int64_t)k;     // written straight from registers (coalesced)
+      double v[SB_NCH];
+#pragma unroll
+      for (int u = 0; u < SB_NCH; ++u) v[u] = (srcc[u] >= 0) ? rrow[srcc[u]] : 0.0;
+      unsigned nf = 0;
+#pragma unroll
+      for (int u = 0; u < SB_NCH; ++u) nf |= ((unsigned)__double2hiint(v[u]) & 0x7ff00000u) == 0x7ff00000u ? 1u : 0u;
+      if (nf) {
+        bad = true;
+        if (do_scrub) {
+#pragma unroll
+          for (int u = 0; u < SB_NCH; ++u) v[u] = scrub(v[u], true, bad);
+        }
+      }
+      if (m.kind == 1) {                                        // force rows: A = R * blank2J (lammps_snap.py:493-502)
+#pragma unroll
+        for (int u = 0; u < SB_NCH; ++u)
+          if (srcc[u] != INT_MIN) orow[lane + 32 * u] = v[u] * pref[u];
+      } else if (m.kind == 2) {                                 // virial rows: (1.6021765e6*R)/V * blank2J (:526-536)
+#pragma unroll
+        for (int u = 0; u < SB_NCH; ++u)
+          if (srcc[u] != INT_MIN) orow[lane + 32 * u] = ((srcc[u] >= 0) ? (VIRIAL_UNIT * v[u]) / m.div : 0.0) * pref[u];
+      } else {                                                  // energy row: R/N (+ type fractions) * blank2J (:435-467)
+#pragma unroll
+        for (int u = 0; u < SB_NCH; ++u)
+          if (srcc[u] != INT_MIN) {
+            const double val = (srcc[u] >= 0) ? v[u] / m.div
+                                              : p.type_fraction[(size_t)m.cfg * p.numtypes + (-srcc[u] - 1)];
+            orow[lane + 32 * u] = val * pref[u];
+          }
+      }
+    }
+    // b and w of the warp's rows (reference column = last raw column)
+    if (lane < SB_RPW) {
+      const int lr = warp * SB_RPW + lane;
+      const SbRowMeta m = s_meta[slot][lr];
+      if (m.kind >= 0) {
+        const double ref = scrub(rin[(size_t)lr * ldr + kraw], do_scrub, bad);
+        p.b[row0 + i0 + lr] = (m.kind == 0) ? (m.truth - ref) / m.div : m.truth - ref;   // :473, :506-507, :540-541
+        p.w[row0 + i0 + lr] = m.wv;
+      }
+    }
+    __syncwarp();
+    if (lane == 0)   // raw slot and its metadata consumed
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bk_smem_u32(&s_empty[slot])) : "memory");
+  }
+  if (p.nonfinite && __any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(p.nonfinite, 1);
+}
+
 }  // namespace
 
 size_t fsb_residual_ws_bytes(const fsb_context* h, int64_t n_rows, int k) {
@@ -768,6 +993,31 @@ int fsb_launch_scatter(const fsb_context* h, const double* raw, const int64_t* r
   a.A = A; a.lda = lda; a.b = b; a.w = w; a.nonfinite = nonfinite; a.row_cfg = row_cfg;
   const bool bzero = flags & FSB_BZEROFLAG;
   const int k = ncoeff * numtypes + (bzero ? 0 : numtypes);
+  {
+    // bulk-copy staged fast path (see scatter_bulk_kernel)
+    static int off = -1;
+    if (off < 0) off = getenv("FSB_SCATTER_NO_BULK") ? 1 : 0;
+    const int all_rows = FSB_ROWS_ENERGY | FSB_ROWS_FORCE | FSB_ROWS_STRESS;
+    if (!off && (flags & all_rows) == all_rows && row_cfg && lda == k && k <= SB_MAXK &&
+        n_rows_hint >= (int64_t)h->sm_count * SB_ROWS * 4) {
+      const int ldr = ncoeff * numtypes + 1;
+      const size_t raw_b = (size_t)SB_ROWS * ldr * sizeof(double);
+      const size_t fixed = 64;
+      int nstage = (int)((h->smem_optin - 2048 - fixed) / raw_b);
+      if (nstage > 6) nstage = 6;
+      if (nstage >= 2) {
+        const size_t smem_b = (size_t)nstage * raw_b + fixed;
+        const int64_t ntiles = fsb_ceil_div(n_rows_hint, SB_ROWS);
+        const int grid = h->sm_count;
+        const int64_t tiles_per_cta = fsb_ceil_div(ntiles, grid);
+        FSB_CUDA_TRY(cudaFuncSetAttribute(scatter_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem_b));
+        scatter_bulk_kernel<<<grid, SB_THREADS, smem_b, s>>>(a, n_rows_hint, tiles_per_cta, nstage);
+        FSB_LAUNCH_CHECK("scatter_bulk_kernel");
+        return FSB_OK;
+      }
+    }
+  }
   const size_t smem = (size_t)k * (sizeof(double) + sizeof(int));
   // tiles of SC_TILE rows, grid-stride; 3 CTAs of 8 warps resident per SM
   int64_t ctas = fsb_ceil_div(n_rows_hint, SC_TILE);

@@ -65,6 +65,45 @@ def test_scatter_bit_exact_vs_reference_fixture(engine, tag):
     assert np.array_equal(w.cpu().numpy(), g["ref_w"])
 
 
+@pytest.mark.parametrize("bz,first_row,nt,nc", [(0, 0, 2, 14), (1, 0, 2, 14), (1, 7, 1, 15)])
+def test_scatter_bulk_staged_path_bit_exact_vs_oracle(engine, bz, first_row, nt, nc):
+    """>= 19k rows with all three row families take scatter_bulk_kernel (TMA-staged): bit-identical to the
+    oracle's restatement of lammps_snap.py:391-556, ragged last tile and a 16-byte-misaligned destination
+    (odd first row x odd width -> the plain load/store branch) included."""
+    from fitsnap_b200.assembly import pack_configs
+    rng = np.random.default_rng(100 + bz + first_row)
+    ncfg = 760
+    kraw = nt * nc
+    k = kraw + (0 if bz else nt)
+    natoms = rng.integers(1, 17, ncfg).astype(np.int32)
+    blocks = [rng.standard_normal((7 + 3 * n, kraw + 1)) for n in natoms]
+    vol = rng.uniform(50, 500, ncfg)
+    energy = rng.normal(-5, 1, ncfg) * natoms
+    forces = [rng.standard_normal((n, 3)) for n in natoms]
+    stress = rng.standard_normal((ncfg, 3, 3)) * 1e3
+    stress = 0.5 * (stress + stress.transpose(0, 2, 1))
+    ew, fw, vw = 10.0 ** rng.uniform(-1, 2, ncfg), 10.0 ** rng.uniform(-1, 1, ncfg), 10.0 ** rng.uniform(-6, -4, ncfg)
+    tf = rng.dirichlet(np.ones(nt), ncfg)
+    b2j = np.ones(k)
+    b2j[rng.choice(k, 3, replace=False)] = 0.0
+    cfgs = [dict(block=blocks[c], natoms=int(natoms[c]), volume=vol[c], energy=energy[c], forces=forces[c],
+                 stress=stress[c], eweight=ew[c], fweight=fw[c], vweight=vw[c], type_fraction=tf[c])
+            for c in range(ncfg)]
+    a, b, w = lf.assemble(cfgs, nt, nc, bz, b2j)
+    assert a.shape[0] >= 19000 and a.shape[0] % 32 != 0
+    batch = pack_configs(engine, np.concatenate(blocks), natoms, vol, energy, np.concatenate(forces), stress, ew, fw,
+                         vw, tf, b2j, nt, nc, bzeroflag=bz, first_row=first_row)
+    n = a.shape[0]
+    A = torch.full((first_row + n, k), -7.0, dtype=torch.float64, device=engine.device)
+    B = torch.full((first_row + n,), -7.0, dtype=torch.float64, device=engine.device)
+    W = torch.full((first_row + n,), -7.0, dtype=torch.float64, device=engine.device)
+    _, _, _, bad = engine.scatter(batch, A, B, W, lda=k)
+    assert int(bad.item()) == 0
+    assert np.array_equal(A[first_row:].cpu().numpy(), a)
+    assert np.array_equal(B[first_row:].cpu().numpy(), b) and np.array_equal(W[first_row:].cpu().numpy(), w)
+    assert bool((A[:first_row] == -7.0).all()) and bool((B[:first_row] == -7.0).all())
+
+
 def test_scatter_padded_lda_and_offset_rows(engine):
     from fitsnap_b200.assembly import pack_configs
     g = load_golden("scatter_snap_b0_efs.npz")
@@ -532,9 +571,13 @@ def test_anl_dropin_matches_reference_fixture(engine, name, tmp_path, monkeypatc
     s.engine = engine
     monkeypatch.chdir(tmp_path)
     s.perform_fit(a=a, b=b, w=w)
+    # anl.py:41-44 inverts the Gram itself: its result moves by ~cond(G + nugget I) * eps when the Gram changes in
+    # the last bit (device summation order vs numpy's), so the tolerance follows the conditioning of the case
+    # ("zerocol": cond ~ 1e13 with nugget 1e-6; the CPU suite pins the same class bit-tight on the reference's Gram)
     mr, l2, _ = lf.coeff_rel_err(s.fit, g["ref_mean"])
-    assert mr < 1e-8, (mr, l2)       # the reference's own pinv-of-Gram mean is only ~cond^2 eps accurate
-    assert np.max(np.abs(s.cov - g["ref_cov"])) < 1e-7 * np.max(np.abs(g["ref_cov"]))
+    tol = 1e-8 if name == "well" else 2e-3
+    assert (mr if name == "well" else l2) < tol, (mr, l2)
+    assert np.max(np.abs(s.cov - g["ref_cov"])) < (1e-7 if name == "well" else 2e-3) * np.max(np.abs(g["ref_cov"]))
     assert s.fit_sam.shape == (3, a.shape[1])
     assert np.array_equal(np.load(tmp_path / "mean.npy"), s.fit)
     assert np.load(tmp_path / "covariance.npy").shape == s.cov.shape
