@@ -9,6 +9,7 @@
 #include "fsb_common.cuh"
 #include <float.h>
 #include <stdlib.h>
+#include <string.h>
 #include <limits.h>
 
 namespace {
@@ -913,6 +914,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1) scatter_bulk_kernel(ScatterArgs
   }
   if (p.nonfinite && __any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(p.nonfinite, 1);
 }
+
 
 }  // namespace
 

@@ -65,13 +65,16 @@ def test_scatter_bit_exact_vs_reference_fixture(engine, tag):
     assert np.array_equal(w.cpu().numpy(), g["ref_w"])
 
 
-@pytest.mark.parametrize("bz,first_row,nt,nc", [(0, 0, 2, 14), (1, 0, 2, 14), (1, 7, 1, 15)])
-def test_scatter_bulk_staged_path_bit_exact_vs_oracle(engine, bz, first_row, nt, nc):
-    """>= 19k rows with all three row families take scatter_bulk_kernel (TMA-staged): bit-identical to the
-    oracle's restatement of lammps_snap.py:391-556, ragged last tile and a 16-byte-misaligned destination
-    (odd first row x odd width -> the plain load/store branch) included."""
+@pytest.mark.parametrize("bz,first_row,nt,nc,efs", [(0, 0, 2, 14, (1, 1, 1)), (1, 0, 2, 14, (1, 1, 1)),
+                                                     (1, 7, 1, 15, (1, 1, 1)), (0, 3, 2, 14, (1, 1, 0)),
+                                                     (1, 0, 2, 70, (0, 1, 1)), (0, 0, 3, 55, (1, 0, 1))])
+def test_scatter_large_batches_bit_exact_vs_oracle(engine, bz, first_row, nt, nc, efs):
+    """Large batches: >= 19k rows with all three row families and k <= 160 take scatter_bulk_kernel (TMA-staged),
+    the others the general tile kernel: bit-identical to the oracle's restatement of lammps_snap.py:391-556 --
+    ragged last tile, odd widths, row offsets (misaligned source / destination), every combination of row
+    families, widths up to 168 columns."""
     from fitsnap_b200.assembly import pack_configs
-    rng = np.random.default_rng(100 + bz + first_row)
+    rng = np.random.default_rng(100 + bz + first_row + nc)
     ncfg = 760
     kraw = nt * nc
     k = kraw + (0 if bz else nt)
@@ -89,10 +92,11 @@ def test_scatter_bulk_staged_path_bit_exact_vs_oracle(engine, bz, first_row, nt,
     cfgs = [dict(block=blocks[c], natoms=int(natoms[c]), volume=vol[c], energy=energy[c], forces=forces[c],
                  stress=stress[c], eweight=ew[c], fweight=fw[c], vweight=vw[c], type_fraction=tf[c])
             for c in range(ncfg)]
-    a, b, w = lf.assemble(cfgs, nt, nc, bz, b2j)
-    assert a.shape[0] >= 19000 and a.shape[0] % 32 != 0
+    a, b, w = lf.assemble(cfgs, nt, nc, bz, b2j, *[bool(v) for v in efs])
+    assert a.shape[0] >= 4096
     batch = pack_configs(engine, np.concatenate(blocks), natoms, vol, energy, np.concatenate(forces), stress, ew, fw,
-                         vw, tf, b2j, nt, nc, bzeroflag=bz, first_row=first_row)
+                         vw, tf, b2j, nt, nc, energy=efs[0], force=efs[1], stress=efs[2], bzeroflag=bz,
+                         first_row=first_row)
     n = a.shape[0]
     A = torch.full((first_row + n, k), -7.0, dtype=torch.float64, device=engine.device)
     B = torch.full((first_row + n,), -7.0, dtype=torch.float64, device=engine.device)
