@@ -37,6 +37,8 @@ WORKLOADS = {
     "c3": dict(ncfg=1841, natoms=64, numtypes=2, ncoeff=239, desc="InP-like 367k x 480 (BASELINE configs[2] shape)"),
     "c5": dict(ncfg=41230, natoms=12, numtypes=2, ncoeff=54, desc="WBe-like 1.77M x 110 (BASELINE configs[4] shape)"),
     "c4s": dict(ncfg=10000, natoms=31, numtypes=2, ncoeff=499, desc="ACE-like 1e6 x 1000 (BASELINE configs[3] shape, 1/10 rows per GPU)"),
+    # the whole BASELINE configs[3] matrix on ONE GPU: 80 GB of raw blocks + 80 GB of A (run with --no-e2e)
+    "c4": dict(ncfg=100000, natoms=31, numtypes=2, ncoeff=499, desc="ACE-like 1e7 x 1000, the full BASELINE configs[3] matrix on one GPU"),
 }
 ALPHA = 1.0e-6
 REFINE = 2
