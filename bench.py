@@ -456,6 +456,15 @@ def main():
                     "peak_kind": "dense bf16 cuBLAS, %s (MEASURED_PEAKS.json)" % peak_kind,
                     "achieved_kind": "algorithmic fp64 flops (2k^2+2k per row, full Gram convention) / Gram time",
                     "hbm_gbs_during_gram": 8.0 * (k + 2) * n_rows / (gram_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak}
+        try:    # ncu-measured DRAM bytes per launch of the dominant kernel, when a capture of this shape is committed
+            tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(
+                "%s:%s" % (args.workload, gram_path))
+            if tr:
+                roofline["traffic"] = tr["bytes_per_launch"]
+                roofline["traffic_note"] = "%s, %d rows x %d: %.3g B from ncu vs %.3g B algorithmic (%s)" % (
+                    tr["kernel"], tr["rows"], tr["k"], tr["bytes_per_launch"], tr["algorithmic_bytes"], tr["source"])
+        except (OSError, ValueError):
+            pass
         if gram_path == "int8":
             n_i = -(-(k + 1) // 128)
             ops = sum(2.0 * 128 * (256 if 2 * jj + 1 < n_i else 128) * n_rows * 16
