@@ -661,12 +661,8 @@ int fsb_launch_gram_i8(const fsb_context* h, const double* A, int64_t lda, const
     FSB_CUDA_TRY(cudaMemsetAsync(gaug, 0, (size_t)ka * ka * sizeof(double), s));
     return FSB_OK;
   }
-  static bool attr_set = false;
   const size_t gemm_smem = (size_t)NST * STAGE_BYTES + 1024;
-  if (!attr_set) {
-    FSB_CUDA_TRY(cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
-    attr_set = true;
-  }
+  FSB_CUDA_TRY(cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
   const int64_t nslab = fsb_ceil_div(n_rows, pl.slab_rows);
   for (int64_t i = 0; i < nslab; ++i) {
     const int64_t r0 = i * pl.slab_rows;

@@ -434,7 +434,7 @@ int launch_rowpass_bulk(const fsb_context* h, const double* A, const double* b, 
   if (npl <= 1) FSB_BULK(1);
   else if (npl <= 2) FSB_BULK(2);
   else if (npl <= 4) FSB_BULK(4);
-  else FSB_BULK(8);
+  else return FSB_ERR_UNSUPPORTED;   // rowpass_bulk_ok admits k <= 128 only
 #undef FSB_BULK
   FSB_LAUNCH_CHECK("rowpass_bulk_kernel");
   *nparts = grid;
