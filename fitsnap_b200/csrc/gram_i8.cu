@@ -12,11 +12,14 @@
 //                         it anyway).  For 16 pairwise coprime moduli p_t <= 256 it writes the symmetric
 //                         residues q mod p_t as int8 planes  R_t[c][r]  (row index contiguous: both MMA
 //                         operands become K-major).  q is split into its 7 low bytes + sign and two
-//                         dp4a instructions per modulus fold them with the byte weights 256^i mod p_t.
+//                         dp4a instructions per modulus fold them with the byte weights 256^i mod p_t; the
+//                         sum is then reduced with three fp32 operations (see I8Tables) -- no division, no
+//                         integer<->float conversion.  No shared memory: a warp owns 4 columns x 128 rows.
 //   3. i8_gemm_kernel     for every modulus and every 128 x 256 tile of the lower triangle:
 //                         C_t = R_t^T R_t  with tcgen05.mma.kind::i8 (M128 N256 K32, int32 accumulators in
 //                         TMEM, operands TMA-loaded with 128-byte swizzle into a 4-stage mbarrier ring; one
-//                         elected thread issues the MMAs, one the TMA loads, four warps drain TMEM).  A unit
+//                         elected thread issues the MMAs, one the TMA loads, four warps drain TMEM; persistent,
+//                         one CTA per SM, two accumulators so that draining overlaps the next unit).  A unit
 //                         covers <= 2^16 rows, so |C_t| <= 2^16 * 128^2 = 2^30 never wraps.  Accumulators are
 //                         added into an int64 table with integer atomics (exact, order-independent).
 //   4. i8_crt_kernel      reduces the table mod p_t, rebuilds the exact integer G'_ij = sum_r q_ri q_rj
@@ -24,7 +27,8 @@
 //                         integers, rounds ONCE to fp64, scales by 2^-(e_i+e_j) and adds the slab into gaug.
 //
 // The result is the correctly rounded Gram of the quantised slab: independent of summation order, tile
-// shape and GPU count, at least as accurate normwise as the DMMA path (tests/test_gpu_parity.py).
+// shape (and, per slab, of the row order), at least as accurate normwise as the DMMA path
+// (tests/test_gpu_gram_int8.py).  Measured: DESIGN.md section 3.1a, profiles/r01_i8_gram_k1000.txt.
 // References: solvers/svd.py:35-53, solvers/ridge.py:28-43 (the products this replaces).
 #include "fsb_common.cuh"
 #include <cuda.h>
