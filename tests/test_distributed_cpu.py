@@ -49,6 +49,38 @@ def test_row_sharded_fit_matches_single_process(tmp_path, case, alpha):
     assert lf.coeff_rel_err(xs[0], ref)[0] < 1e-10
 
 
+def _anl_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from types import SimpleNamespace
+    from fitsnap_b200.solvers import ANL
+    from tests.fake_engine import OracleEngine
+    a, b, w, t = synth_system(**SOLVE_CASES["well"])
+    lo, hi = shard_rows(a.shape[0], world, rank)
+    pt = SimpleNamespace(_rank=rank, shared_arrays={}, fitsnap_dict={"Testing": [bool(v) for v in t[lo:hi]]})
+    cfg = SimpleNamespace(sections={"SOLVER": SimpleNamespace(cov_nugget=1e-8, nsam=0)})
+    s = ANL("ANL", pt, cfg)
+    s.engine = OracleEngine()
+    s.process_group = dist.group.WORLD
+    s.save_files = False
+    s.perform_fit(a=a[lo:hi], b=b[lo:hi], w=w[lo:hi])
+    np.savez(os.path.join(out_dir, "anl_%d.npz" % rank), mean=s.fit, cov=s.cov)
+    dist.destroy_process_group()
+
+
+def test_row_sharded_anl_matches_single_process(tmp_path):
+    """ANL over two row shards: all-reduced Gram and all-reduced residual sums give the single-process
+    posterior mean and covariance (anl.py:40-58) on every rank."""
+    world = 2
+    mp.spawn(_anl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    out = [np.load(tmp_path / ("anl_%d.npz" % r)) for r in range(world)]
+    assert np.array_equal(out[0]["mean"], out[1]["mean"]) and np.array_equal(out[0]["cov"], out[1]["cov"])
+    a, b, w, t = synth_system(**SOLVE_CASES["well"])
+    mean, cov = lf.anl_fit(a, b, w, 1e-8, t)
+    assert np.max(np.abs(out[0]["mean"] - mean)) < 1e-9 * np.max(np.abs(mean))
+    assert np.max(np.abs(out[0]["cov"] - cov)) < 1e-7 * np.max(np.abs(cov))
+
+
 def test_shard_rows_partition():
     for n in (0, 1, 7, 1000, 1001):
         for world in (1, 2, 3, 8):
