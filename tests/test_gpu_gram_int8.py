@@ -136,3 +136,19 @@ def test_int8_fit_matches_reference_solvers(engine8, name):
     x = engine8.fit(A, B, W, T, alpha=alpha, refine=2).coefficients()
     mr, l2, _ = lf.coeff_rel_err(x, lf.ridge_fit_exact(a, b, w, alpha, t))
     assert mr < 1e-10, (mr, l2)
+
+
+@pytest.mark.parametrize("n,k", [(3000, 45), (270000, 3)])
+def test_int8_gram_bit_exact_vs_integer_oracle(engine8, n, k):
+    """Integer work has a bit-exact bar: the device Gram (16 residue GEMMs on the tensor cores + CRT) must equal
+    the exact-integer restatement in oracle/int8_gram.py bit for bit -- wide weights, a test mask, and (second
+    case) two slabs with their own column scales."""
+    from oracle.int8_gram import quantised_gram
+    rng = np.random.default_rng(n + k)
+    a = rng.standard_normal((n, k)) * 10.0 ** rng.uniform(-4, 1, k)
+    b = rng.standard_normal(n)
+    w = 10.0 ** rng.uniform(-12, 3.2, n)
+    t = rng.random(n) < 0.1
+    A, B, W, T = dev(engine8, a, b, w, t)
+    g = engine8.gram(A, B, W, T).cpu().numpy()
+    assert np.array_equal(g, quantised_gram(a, b, w, t))

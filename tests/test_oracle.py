@@ -95,3 +95,25 @@ def test_oracle_anl_matches_reference_fixture(name):
     mean, cov = lf.anl_fit(a, b, w, float(g["cov_nugget"]), t)
     assert np.max(np.abs(mean - g["ref_mean"])) <= 1e-9 * np.max(np.abs(g["ref_mean"]))
     assert np.max(np.abs(cov - g["ref_cov"])) <= 1e-8 * np.max(np.abs(g["ref_cov"]))
+
+
+def test_int8_gram_oracle_is_the_correctly_rounded_quantised_gram():
+    """oracle/int8_gram.py (exact-integer statement of the tensor-core Gram): equals aw^T aw within half an ulp-ish of
+    an extended-precision product, is EXACT on dyadic inputs, and follows the device's slab rule."""
+    from oracle.int8_gram import quantised_gram, slab_rows_for
+    rng = np.random.default_rng(0)
+    n, k = 1500, 20
+    a = rng.standard_normal((n, k)) * 10.0 ** rng.uniform(-3, 0, k)
+    b, w = rng.standard_normal(n), 10.0 ** rng.uniform(-2, 2, n)
+    t = rng.random(n) < 0.2
+    g = quantised_gram(a, b, w, t)
+    aw, bw = lf.weighted_system(a, b, w, t)
+    aug = np.concatenate([aw, bw[:, None]], 1).astype(np.longdouble)
+    exact = np.asarray(aug.T @ aug, dtype=np.float64)
+    d = np.sqrt(np.diag(exact))
+    assert np.max(np.abs(g - exact) / np.outer(d, d)) < 1e-15 and np.array_equal(g, g.T)
+    a2 = rng.integers(-1000, 1001, (300, 7)).astype(float) * 2.0 ** rng.integers(-20, 20, 7)
+    b2, w2 = rng.integers(-50, 51, 300).astype(float), 2.0 ** rng.integers(-3, 4, 300)
+    aug2 = np.concatenate([a2 * w2[:, None], (w2 * b2)[:, None]], 1)
+    assert np.array_equal(quantised_gram(a2, b2, w2), aug2.T @ aug2)
+    assert slab_rows_for(1) == 128 and slab_rows_for(262144) == 262144 and slab_rows_for(600000) == 200064
