@@ -41,6 +41,23 @@ class LinearFitPipeline:
         res.extra.update(A=A, b=b, w=w, nonfinite=bad)
         return res
 
+    def fit_stream(self, batches, refine=None) -> FitResult:
+        """Out-of-core variant of `fit_host`: `batches` is a re-iterable (list, or callable returning an iterator) of
+        argument tuples of `pack` (blocks, natoms, volumes, energies, forces, stresses, eweights, fweights, vweights[,
+        type_fraction]); every batch is uploaded, scattered into rows and folded into the running Gram / residual
+        (see StreamingLinearFit), so neither the raw blocks nor A are ever resident as a whole."""
+        eng = self.engine
+
+        def rows():
+            for args in StreamingLinearFit._iterate(batches):
+                batch = self.pack(*args)
+                A, b, w, bad = eng.scatter(batch)
+                if int(bad.item()) and not self.scrub:
+                    raise ValueError("Nan in computed data")     # lammps_snap.py:426-428
+                yield A, b, w
+        sf = StreamingLinearFit(self.alpha, self.refine if refine is None else refine, self.group, eng)
+        return sf.fit(rows)
+
     def capture(self, batch: ConfigBatch, testing=None, out=None, warmup=2) -> "CapturedStep":
         """CUDA graph of one device-resident step over fixed buffers (see CapturedStep)."""
         return CapturedStep(self, batch, testing, out, warmup)
@@ -136,6 +153,90 @@ class LinearFitPipeline:
         summary = SimpleNamespace(ncfg=ncfg, k=k, row_begin=0, row_end=n_out, n_rows_out=n_out, h2d_bytes=int(h2d),
                                   chunks=len(batches))
         return x, res, summary
+
+
+class StreamingLinearFit:
+    """Out-of-core fit: the design matrix is never resident as a whole (the mode of
+    examples/library/transpose_trick/example.py:226-246, where C += a^T a, d += a^T b per configuration).
+
+    `chunks` is a RE-ITERABLE of row chunks -- a list, or a zero-argument callable returning a fresh iterator --
+    each `(a, b, w)` or `(a, b, w, testing)`, host numpy or device tensors.  Pass 0 accumulates the augmented Gram
+    chunk by chunk (one `fsb_gram` per chunk, summed on the device), all-reduces it once, factors and solves; each
+    refinement round streams the chunks again and accumulates `aw^T (bw - aw x)` (one `fsb_residual` per chunk, one
+    k-vector all-reduce per round).  Device memory: one chunk + O(k^2).  The result equals `Engine.fit` on the
+    stacked rows up to the summation order of the chunk Grams."""
+
+    def __init__(self, alpha=0.0, refine=2, group=None, engine: Engine | None = None):
+        self.engine = engine or default_engine()
+        self.alpha, self.refine, self.group = float(alpha), int(refine), group
+
+    @staticmethod
+    def _iterate(chunks):
+        return iter(chunks() if callable(chunks) else chunks)
+
+    def _device_chunk(self, chunk):
+        eng = self.engine
+        a, b, w = chunk[0], chunk[1], chunk[2]
+        t = chunk[3] if len(chunk) > 3 else None
+        A = eng.to_device(a)
+        B = eng.to_device(b).reshape(-1)
+        W = eng.to_device(w).reshape(-1)
+        T = None
+        if t is not None:
+            T = t.to(eng.device, torch.uint8) if isinstance(t, torch.Tensor) else \
+                eng.to_device(np.ascontiguousarray(t, dtype=np.uint8), dtype=torch.uint8)
+        return A, B, W, T
+
+    def fit(self, chunks) -> FitResult:
+        from .engine import _all_reduce
+        eng = self.engine
+        start = getattr(eng, "launch_count", 0)
+        gaug, n_rows = None, 0
+        for chunk in self._iterate(chunks):
+            A, B, W, T = self._device_chunk(chunk)
+            g = eng.gram(A, B, W, T)
+            gaug = g if gaug is None else gaug.add_(g)
+            n_rows += int(A.shape[0])
+        if gaug is None:
+            raise ValueError("StreamingLinearFit.fit: no chunks")
+        _all_reduce(gaug, self.group)
+        k = gaug.shape[0] - 1
+        f = eng.factor(gaug, self.alpha)
+        x = eng.solve(f, gaug[:, k], rhs_stride=k + 1)
+        for _ in range(self.refine):
+            gsum = None
+            for chunk in self._iterate(chunks):
+                A, B, W, T = self._device_chunk(chunk)
+                g = eng.residual(A, B, W, T, x)
+                gsum = g if gsum is None else gsum.add_(g)
+            _all_reduce(gsum, self.group)
+            x = eng.solve(f, gsum, x_in=x)
+        return FitResult(x=x, gaug=gaug, info=f.info, launches=getattr(eng, "launch_count", 0) - start,
+                         extra={"factor": f, "rows_streamed": n_rows})
+
+
+def npy_row_chunks(descriptors, truth, weights, chunk_rows=1 << 20, testing=None):
+    """Re-iterable over the `.npy` dumps FitSNAP writes with `[EXTRAS] dump_descriptors / dump_truth /
+    dump_weights` (calculators/calculator.py:329-337; default names Descriptors.npy, Truth-Ref.npy, Weights.npy,
+    io/sections/extras.py:32-37), memory-mapped: feed it to `StreamingLinearFit.fit` to refit dumped matrices
+    that do not fit in device (or host) memory.  `testing`: optional bool array / list over all rows."""
+    def factory():
+        a = np.load(descriptors, mmap_mode="r")
+        b = np.load(truth, mmap_mode="r")
+        w = np.load(weights, mmap_mode="r")
+        if a.ndim == 1:
+            a = a.reshape(-1, 1)
+        n = a.shape[0]
+        if b.shape[0] != n or w.shape[0] != n:
+            raise ValueError("row counts differ: %s %s %s" % (a.shape, b.shape, w.shape))
+        t = None if testing is None else np.asarray(testing, dtype=bool)
+        for r0 in range(0, n, int(chunk_rows)):
+            r1 = min(n, r0 + int(chunk_rows))
+            # copies out of the (read-only) memory maps: the upload pins them anyway
+            out = (np.array(a[r0:r1], dtype=np.float64), np.array(b[r0:r1], dtype=np.float64),
+                   np.array(w[r0:r1], dtype=np.float64))
+            yield out if t is None else out + (t[r0:r1],)
+    return factory
 
 
 class CapturedStep:

@@ -24,6 +24,10 @@ class OracleEngine:
             return arr.to(dtype)
         return torch.from_numpy(np.ascontiguousarray(arr)).to(dtype)
 
+    def fit(self, A, b, w, testing=None, alpha=0.0, refine=2, group=None, diagnostics=True):
+        from fitsnap_b200.engine import fit_rows
+        return fit_rows(self, A, b, w, testing, alpha=alpha, refine=refine, group=group, diagnostics=diagnostics)
+
     def scatter(self, batch, A=None, b=None, w=None, lda=None):
         """Row assembly through the oracle (lammps_snap.py:391-556 restated in oracle/linear_fit.py)."""
         nat = batch.natoms.numpy()

@@ -585,3 +585,21 @@ def test_anl_dropin_matches_reference_fixture(engine, name, tmp_path, monkeypatc
     assert s.fit_sam.shape == (3, a.shape[1])
     assert np.array_equal(np.load(tmp_path / "mean.npy"), s.fit)
     assert np.load(tmp_path / "covariance.npy").shape == s.cov.shape
+
+
+def test_streaming_fit_on_device_matches_reference(engine, ta, tmp_path):
+    """Out-of-core mode on the real kernels: the golden Ta dumps streamed in 4 chunks from .npy files, and a
+    masked synthetic system in ragged chunks, against the reference solvers."""
+    from fitsnap_b200.pipeline import StreamingLinearFit, npy_row_chunks
+    np.save(tmp_path / "Descriptors.npy", ta["a"])
+    np.save(tmp_path / "Truth-Ref.npy", ta["b"])
+    np.save(tmp_path / "Weights.npy", ta["w"])
+    chunks = npy_row_chunks(tmp_path / "Descriptors.npy", tmp_path / "Truth-Ref.npy", tmp_path / "Weights.npy",
+                            chunk_rows=4000)
+    res = StreamingLinearFit(alpha=0.0, refine=2, engine=engine).fit(chunks)
+    assert lf.coeff_rel_err(res.coefficients(), ta["ref_svd"])[0] < 1e-10
+    a, b, w, t = synth_system(**SOLVE_CASES["ill"])
+    cuts = [0, 1000, 1001, 4200, a.shape[0]]
+    parts = [(a[i:j], b[i:j], w[i:j], t[i:j]) for i, j in zip(cuts[:-1], cuts[1:])]
+    res = StreamingLinearFit(alpha=1e-6, refine=2, engine=engine).fit(parts)
+    assert lf.coeff_rel_err(res.coefficients(), lf.ridge_fit_exact(a, b, w, 1e-6, t))[0] < 1e-10
