@@ -47,7 +47,7 @@ constexpr int FSB_GTHREADS = 512;    // 16 warps, each owning a 32x32 sub-tile (
 // FSB_GRAM_AUTO switches to the int8 tcgen05 Gram from this shape on (gram.cu: fsb_gram_path_for)
 // (measured crossover against the DMMA path: ~250 columns; 1.7x at 480, 2.3x at 1000 columns)
 constexpr int FSB_I8_AUTO_MIN_COLS = 384;
-constexpr int64_t FSB_I8_AUTO_MIN_ROWS = 32768;
+constexpr int64_t FSB_I8_AUTO_MIN_ROWS = 65536;   // 30000 x 1000 measured 0.9x, 1e6 x 1000 2.3x
 
 // Cholesky panel width
 constexpr int FSB_NB = 64;

@@ -284,7 +284,8 @@ class ANL(LinearSolverBase):
     training row count (`fsb_group_stats`).  Everything between them is k x k algebra on the all-reduced Gram and
     is kept as anl.py:41-44 states it (numpy `pinv`, default rcond 1e-15 ON THE EIGENVALUES of the Gram, i.e. a
     rank truncation at sigma/sigma_max ~ 3e-8 -- replacing it by the refined Cholesky solve of the SVD/RIDGE
-    drop-ins would change the answer whenever that truncation bites)."""
+    drop-ins would change the answer whenever that truncation bites).  `[EXTRAS] apply_transpose` (anl.py:32-37,
+    marked "probably nonsense" there: it squares the Gram and ends with a negative variance) is not mirrored."""
 
     #: write covariance.npy / mean.npy like the reference (tests switch it off)
     save_files = True
