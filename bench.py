@@ -306,23 +306,28 @@ def main():
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    phase_ev = []
     for _ in range(args.steps):
-        # the step, with CUDA events bracketing the Gram launch on its own (current) stream
+        # the step, with CUDA events between its phases on the stream the kernels are launched on
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
         Ad, bd, wd, _bad = eng.scatter(batch, *out)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
+        ev[1].record()
         gaug = eng.gram(Ad, bd, wd, None)
-        g1.record()
-        gram_ev.append((g0, g1))
+        ev[2].record()
+        gram_ev.append((ev[1], ev[2]))
         if world > 1:
             dist.all_reduce(gaug, group=group)
         f = eng.factor(gaug, ALPHA)
         x = eng.solve(f, gaug[:, k], rhs_stride=k + 1)
+        ev[3].record()
         for _r in range(REFINE):
             g = eng.residual(Ad, bd, wd, None, x)
             if world > 1:
                 dist.all_reduce(g, group=group)
             x = eng.solve(f, g, x_in=x)
+        ev[4].record()
+        phase_ev.append(ev)
     e1.record()
     torch.cuda.synchronize()
     barrier()
@@ -335,6 +340,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     ms_step = float(t.item())
     gram_ms = float(np.mean([a_.elapsed_time(b_) for a_, b_ in gram_ev]))
+    names = ("scatter", "gram", "allreduce_factor_solve", "refine_%dx(residual+allreduce+solve)" % REFINE)
+    phases_ms = {nm: float(np.mean([ev[i].elapsed_time(ev[i + 1]) for ev in phase_ev])) for i, nm in enumerate(names)}
+    phase_rows_per_s = {nm: n_rows / (ms * 1e-3) for nm, ms in phases_ms.items() if ms > 0}
     value = world * n_rows / (ms_step / 1e3)
 
     # ---- the same step replayed from a CUDA graph (one cudaGraphLaunch instead of `launches` launches) ----
@@ -496,6 +504,8 @@ def main():
                              (n_rows * k * 8 / 1e6, n_rows * (kraw + 1) * 8 / 1e6)},
             "gram_tflops_algorithmic": achieved,
             "gram_ms": gram_ms,
+            "phases_ms_rank0": phases_ms,
+            "phase_rows_per_s_per_gpu": phase_rows_per_s,
             "roofline": roofline,
             "coeff_max_rel_err": coeff_err,
             "cpu_baseline": cpu_baseline,
