@@ -108,6 +108,40 @@ def test_scatter_large_batches_bit_exact_vs_oracle(engine, bz, first_row, nt, nc
     assert bool((A[:first_row] == -7.0).all()) and bool((B[:first_row] == -7.0).all())
 
 
+def test_scatter_large_batch_nonfinite_detection_and_scrub(engine):
+    """The TMA-staged scatter keeps the NaN/Inf contract of the general kernel: a non-finite raw value is counted
+    (lammps_snap.py:426-428 raises from it), and with the scrub flag it is replaced as numpy.nan_to_num does
+    (lammps_pace.py:399-403) -- checked against the oracle on a >= 19k-row batch."""
+    from fitsnap_b200.assembly import pack_configs
+    rng = np.random.default_rng(77)
+    nt, nc, ncfg = 2, 14, 760
+    kraw, k = nt * nc, nt * nc + nt
+    natoms = rng.integers(1, 17, ncfg).astype(np.int32)
+    blocks = [rng.standard_normal((7 + 3 * n, kraw + 1)) for n in natoms]
+    blocks[300][2, 5] = np.nan
+    blocks[700][0, 1] = np.inf
+    blocks[10][4, kraw] = -np.inf                      # reference column of a force row
+    vol = rng.uniform(50, 500, ncfg)
+    energy = rng.normal(-5, 1, ncfg) * natoms
+    forces = [rng.standard_normal((n, 3)) for n in natoms]
+    stress = rng.standard_normal((ncfg, 3, 3))
+    stress = 0.5 * (stress + stress.transpose(0, 2, 1))
+    ew, fw, vw = np.ones(ncfg), np.ones(ncfg), np.full(ncfg, 1e-4)
+    tf = rng.dirichlet(np.ones(nt), ncfg)
+    b2j = np.ones(k)
+    args = (np.concatenate(blocks), natoms, vol, energy, np.concatenate(forces), stress, ew, fw, vw, tf, b2j, nt, nc)
+    _, _, _, bad = engine.scatter(pack_configs(engine, *args, bzeroflag=False))
+    assert int(bad.item()) > 0
+    A, B, W, bad = engine.scatter(pack_configs(engine, *args, bzeroflag=False, scrub_nonfinite=True))
+    assert int(bad.item()) > 0 and bool(torch.isfinite(A).all()) and bool(torch.isfinite(B).all())
+    cfgs = [dict(block=np.nan_to_num(blocks[c]), natoms=int(natoms[c]), volume=vol[c], energy=energy[c],
+                 forces=forces[c], stress=stress[c], eweight=ew[c], fweight=fw[c], vweight=vw[c], type_fraction=tf[c])
+            for c in range(ncfg)]
+    a, b, w = lf.assemble(cfgs, nt, nc, 0, b2j)
+    assert a.shape[0] >= 19000
+    assert np.array_equal(A.cpu().numpy(), a) and np.array_equal(B.cpu().numpy(), b)
+
+
 def test_scatter_padded_lda_and_offset_rows(engine):
     from fitsnap_b200.assembly import pack_configs
     g = load_golden("scatter_snap_b0_efs.npz")
