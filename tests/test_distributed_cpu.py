@@ -81,6 +81,31 @@ def test_row_sharded_anl_matches_single_process(tmp_path):
     assert np.max(np.abs(out[0]["cov"] - cov)) < 1e-7 * np.max(np.abs(cov))
 
 
+def _stream_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fitsnap_b200.pipeline import StreamingLinearFit
+    from tests.fake_engine import OracleEngine
+    a, b, w, t = synth_system(**SOLVE_CASES["ill"])
+    lo, hi = shard_rows(a.shape[0], world, rank)
+    cuts = np.linspace(lo, hi, 4 + rank).astype(int)          # a different number of chunks on every rank
+    chunks = [(a[i:j], b[i:j], w[i:j], t[i:j]) for i, j in zip(cuts[:-1], cuts[1:])]
+    res = StreamingLinearFit(alpha=1e-6, refine=2, group=dist.group.WORLD, engine=OracleEngine()).fit(chunks)
+    np.save(os.path.join(out_dir, "xs_%d.npy" % rank), res.x.numpy())
+    dist.destroy_process_group()
+
+
+def test_row_sharded_streaming_fit_matches_single_process(tmp_path):
+    """Out-of-core mode under sharding: every rank streams its own rows in its own chunking; one all-reduce of the
+    accumulated Gram and one per refinement round."""
+    world = 2
+    mp.spawn(_stream_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    xs = [np.load(tmp_path / ("xs_%d.npy" % r)) for r in range(world)]
+    assert np.array_equal(xs[0], xs[1])
+    a, b, w, t = synth_system(**SOLVE_CASES["ill"])
+    assert lf.coeff_rel_err(xs[0], lf.ridge_fit_exact(a, b, w, 1e-6, t))[0] < 1e-10
+
+
 def test_shard_rows_partition():
     for n in (0, 1, 7, 1000, 1001):
         for world in (1, 2, 3, 8):
