@@ -197,6 +197,7 @@ class _CollectMixin:
         if col is None or not col.natoms:
             return
         first = self._b200_first_row
+        self._check_device_memory(col)
         A, b, w, bad, batch = col.flush(first_row=0)
         n = batch.n_rows_out
         sa = self.pt.shared_arrays
@@ -211,6 +212,21 @@ class _CollectMixin:
         self.pt.fitsnap_b200_device = {"A": A, "b": b, "w": w, "first_row": first, "n_rows": n}
         col.reset()
         self._b200_col = None
+
+    def _check_device_memory(self, col):
+        """Device-side twin of the reference's RAM guard (calculator.py:277-285): the raw blocks and A, b, w of this
+        rank must not take more than half of the GPU unless `[MEMORY] override = 1`."""
+        mem = getattr(col.engine, "device_memory", None)
+        if mem is None:
+            return
+        _free, total = mem()
+        need = 8 * (col._nraw * (col.kraw + 1) + col.n_out * (col.k + 2))
+        if need / total > 0.5:
+            msec = self.config.sections["MEMORY"] if "MEMORY" in getattr(self.config, "sections", {}) else None
+            if not getattr(msec, "override", False):
+                raise MemoryError("The descriptor matrix and its raw blocks (%.1f GB) are larger than 50%% of the "
+                                  "GPU memory (%.1f GB). \n Aborting...!" % (need * 1e-9, total * 1e-9))
+            self.pt.single_print("Warning: > 50 % of the GPU memory. I hope you know what you are doing!")
 
     def collect_distributed_lists(self, allgather=False):
         self.flush_to_shared_arrays()

@@ -92,6 +92,10 @@ class Engine:
             self._ws[tag] = t
         return t
 
+    def device_memory(self):
+        """(free, total) bytes of this engine's GPU."""
+        return torch.cuda.mem_get_info(self.device)
+
     def to_device(self, arr, dtype=torch.float64, non_blocking=True):
         """Host numpy -> device tensor through pinned memory (or pass a device tensor through)."""
         if isinstance(arr, torch.Tensor):

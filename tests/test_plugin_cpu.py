@@ -162,3 +162,29 @@ def test_coefficient_file_round_trip(registered):
             pos += 1
     parsed = np.array(parsed)
     assert np.max(np.abs(parsed - fit)) <= 1e-17 * np.max(np.abs(fit)) + 1e-300
+
+
+def test_device_memory_guard_mirrors_the_reference_ram_guard(registered):
+    """calculator.py:277-285 aborts when A exceeds half of the RAM unless [MEMORY] override; the drop-in applies the
+    same rule to the GPU that will hold the raw blocks and A, b, w."""
+    from tests.fake_engine import OracleEngine
+
+    class TinyGpu(OracleEngine):
+        def device_memory(self):
+            return 1000, 4000           # bytes: anything staged is "too large"
+
+    rng = np.random.default_rng(4)
+    kw = dict(numtypes=1, types="Ta", twojmax="4", bzeroflag=0)
+    pt0, cfg0 = rd.make_reference_context(**kw)
+    nc = cfg0.sections["BISPECTRUM"].ncoeff
+    cfgs, blocks, vols = _configs(rng, nc, 1, n_cfg=5)
+    ctx = rd.make_reference_context(**kw)
+    from fitsnap_b200 import plugin
+    plugin.unregister()
+    plugin.register(engine=TinyGpu())
+    with pytest.raises(MemoryError, match="GPU memory"):
+        rd.ref_scatter(cfgs, blocks, vols, use_factory=True, context=ctx, **kw)
+    pt, cfg = rd.make_reference_context(**kw)
+    cfg.sections["MEMORY"].override = True
+    a, *_ = rd.ref_scatter(cfgs, blocks, vols, use_factory=True, context=(pt, cfg), **kw)
+    assert a.shape[0] > 0
