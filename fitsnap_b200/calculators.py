@@ -3,6 +3,8 @@
 Reference interface being mirrored (paths relative to the FitSNAP tree):
     calculators/lammps_snap.py:391-556  LammpsSnap._collect_lammps   (rows of A, b, w + row metadata)
     calculators/lammps_pace.py:369-509  LammpsPace._collect_lammps
+    calculators/lammps_snap.py:224-389  LammpsSnap._collect_lammps_single  (process_single, lammps_base.py:101-125)
+    calculators/lammps_pace.py:197-366  LammpsPace._collect_lammps_single
     calculators/calculator.py:261-299   Calculator.create_a (linear branch: a_len, shared arrays)
     calculators/calculator.py:311-326   Calculator.collect_distributed_lists
 
@@ -23,6 +25,7 @@ import numpy as np
 import torch
 
 from .assembly import descriptor_width, pack_configs, rows_per_config, type_fractions
+from .hostmirror import LazyHostMirror
 
 
 def extract_compute_array(lmp, name, shape):
@@ -161,7 +164,26 @@ class _CollectMixin:
             self._b200_first_row = self.shared_index
         return col
 
-    def _collect_lammps(self):
+    def _b200_stock_mode(self):
+        """True for the layouts the batched scatter does not cover: per-atom energy rows (`bikflag`, N energy
+        rows per configuration, lammps_snap.py:409-411, 430-433), descriptor-gradient output (`dgradflag`),
+        `[CALCULATOR] per_atom_energy` and the nonlinear (network) branch.  Those configurations are handed to
+        the reference's own `_collect_lammps*` (kept on the class by plugin.register) -- never reinterpreted."""
+        sec = self.config.sections[self.SECTION]
+        calc = self.config.sections["CALCULATOR"]
+        return bool(getattr(sec, "bikflag", 0) or getattr(sec, "dgradflag", 0) or
+                    getattr(calc, "per_atom_energy", False) or getattr(calc, "nonlinear", False))
+
+    def _b200_stock(self, name):
+        fn = getattr(self, "_ref_" + name.lstrip("_"), None)
+        if fn is None:
+            raise NotImplementedError(
+                "fitsnap_b200: bikflag / dgradflag / per_atom_energy / nonlinear layouts are assembled by the "
+                "reference's own %s, which is only available after fitsnap_b200.plugin.register()" % name)
+        return fn()
+
+    def _b200_gather_block(self):
+        """What both `_collect_lammps` variants read from LAMMPS (lammps_snap.py:393-428)."""
         d = self._data
         n = d["NumAtoms"]
         sec = self.config.sections[self.SECTION]
@@ -178,6 +200,53 @@ class _CollectMixin:
             self.pt.single_print("! WARNING! applying np.nan_to_num()")     # lammps_pace.py:399-401
         if calc.energy:
             self._warn_if_no_neighbors(block, n, sec, d)
+        return d, n, sec, calc, lmp_types, volume, block
+
+    def _collect_lammps_single(self):
+        """`process_single` body (lammps_base.py:101-125 -> lammps_snap.py:224-389 / lammps_pace.py:197-366):
+        rows of ONE configuration returned as host `(a, b, w)`, shared arrays untouched.  Layout quirk kept from
+        the reference: `a` always has the energy row and the 3N force rows (plus the 6 virial rows iff
+        `[CALCULATOR] stress`), and the rows of a switched-off family stay zero (`irow` advances regardless,
+        lammps_snap.py:341, 364); missing `eweight`/`fweight`/`vweight` keys default to 1.0 (:337, 360, 383).
+        The arithmetic runs in the same scatter kernel as the batched path."""
+        if self._b200_stock_mode():
+            return self._b200_stock("_collect_lammps_single")
+        d, n, sec, calc, lmp_types, volume, block = self._b200_gather_block()
+        col = getattr(self, "_b200_single_col", None)
+        if col is None:
+            from .engine import default_engine
+            eng = getattr(self, "_b200_engine", None) or default_engine()
+            col = BlockCollector(eng, sec.numtypes, sec.ncoeff, sec.bzeroflag, np.asarray(sec.blank2J, dtype=np.float64),
+                                 sec.type_mapping, calc.energy, calc.force, calc.stress, scrub_nonfinite=self.SCRUB,
+                                 capacity_rows=1 + 3 * n + 6)
+            self._b200_single_col = col
+        col.reset()
+        e, f, s = col.rows
+        na = 1 + 3 * n + (6 if s else 0)
+        a = np.zeros((na, col.k))
+        b = np.zeros(na)
+        w = np.zeros(na)
+        nrows = col.add(block, n, volume, d["Energy"], d["Forces"], d["Stress"], d.get("eweight", 1.0),
+                        d.get("fweight", 1.0), d.get("vweight", 1.0), d["AtomTypes"])
+        if nrows:
+            A_d, b_d, w_d, _bad, _batch = col.flush(first_row=0)
+            A_h, b_h, w_h = A_d.cpu().numpy(), b_d.cpu().numpy(), w_d.cpu().numpy()
+            src = 0
+            for on, dst0, cnt in ((e, 0, 1), (f, 1, 3 * n), (s, 1 + 3 * n, 6)):
+                if on:
+                    a[dst0:dst0 + cnt] = A_h[src:src + cnt]
+                    b[dst0:dst0 + cnt] = b_h[src:src + cnt]
+                    w[dst0:dst0 + cnt] = w_h[src:src + cnt]
+                    src += cnt
+        col.reset()
+        self.shared_index = nrows                      # lammps_snap.py:386-387 (`index` restarts at 0)
+        self.distributed_index += nrows
+        return a, b, w
+
+    def _collect_lammps(self):
+        if self._b200_stock_mode():
+            return self._b200_stock("_collect_lammps")
+        d, n, sec, calc, lmp_types, volume, block = self._b200_gather_block()
         col = self._b200_collector()
         nrows = col.add(block, n, volume, d["Energy"], d["Forces"], d["Stress"], d["eweight"], d["fweight"],
                         d["vweight"], d["AtomTypes"])
@@ -200,15 +269,17 @@ class _CollectMixin:
         self._check_device_memory(col)
         A, b, w, bad, batch = col.flush(first_row=0)
         n = batch.n_rows_out
-        sa = self.pt.shared_arrays
-        a_host = sa["a"].array
-        if a_host.ndim == 1:
-            a_host = a_host.reshape(-1, 1)
-        a_host[first:first + n] = A.cpu().numpy()
-        sa["b"].array[first:first + n] = b.cpu().numpy()
-        sa["w"].array[first:first + n] = w.cpu().numpy()
         if int(bad.item()) and not self.SCRUB:
             raise ValueError("Nan in computed data")
+        # the host mirror is filled lazily: the copy of A back to the host only happens if somebody reads
+        # pt.shared_arrays[...].array (dumps, library users, the stock error analysis); see hostmirror.py
+        sa = self.pt.shared_arrays
+        eager = bool(getattr(self, "b200_eager_host_mirror", False))
+        for name, dev_t in (("a", A), ("b", b), ("w", w)):
+            inner = sa[name].unwrap() if isinstance(sa[name], LazyHostMirror) else sa[name]
+            sa[name] = LazyHostMirror(inner, dev_t, first, n)
+            if eager:
+                sa[name].materialize()
         self.pt.fitsnap_b200_device = {"A": A, "b": b, "w": w, "first_row": first, "n_rows": n}
         col.reset()
         self._b200_col = None

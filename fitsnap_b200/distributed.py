@@ -37,3 +37,36 @@ def shard_configs_by_rows(rows_per_config, world):
         bounds.append(min(max(j, bounds[-1]), len(rows)))
     bounds.append(len(rows))
     return np.asarray(bounds, dtype=np.int64)
+
+
+def attach(target, group=None, engine=None):
+    """Make the drop-in solver (and calculator) of `target` row-sharded over `group`.
+
+    `target` is a `FitSnap` instance (its `.solver` / `.calculator` are used) or a solver object.  One process per
+    GPU: every rank runs the reference's flow over ITS OWN configurations (the way every MPI rank of the reference
+    assembles its own row block, parallel_tools.py:594-651), the rows stay on that rank's GPU, and
+    `solver.perform_fit()` -- which the reference already calls on every rank (fitsnap.py:198-200) -- forms the local
+    Gram, all-reduces the (k+1)^2 doubles once and solves the replicated k x k system; `solver.fit` ends up identical
+    on every rank.  `error_analysis()` all-reduces the per-group sums the same way.
+
+        torch.distributed.init_process_group("nccl")           # torchrun exports RANK / LOCAL_RANK / WORLD_SIZE
+        plugin.register()
+        fs = FitSnap(settings, comm=None, arglist=["--overwrite"])
+        distributed.attach(fs)                                  # binds LOCAL_RANK -> GPU, sets solver.process_group
+        fs.process_configs(data=my_share_of_the_configurations)
+        fs.perform_fit()
+    """
+    import torch.distributed as dist
+    from .engine import default_engine
+    if group is None:
+        if not dist.is_initialized():
+            raise RuntimeError("attach(): torch.distributed is not initialised and no process group was given")
+        group = dist.group.WORLD
+    eng = engine or default_engine()
+    solver = getattr(target, "solver", target)
+    solver.process_group = group
+    solver.engine = eng
+    calc = getattr(target, "calculator", None)
+    if calc is not None:
+        calc._b200_engine = eng
+    return solver

@@ -11,6 +11,8 @@ Path: a5 mask+weight -> a6/a7/a8 Gram + factor + solve (+ refinement
 from __future__ import annotations
 
 import ctypes
+import os
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -54,6 +56,61 @@ class FitResult:
         return self.info.detach().cpu().numpy()
 
 
+_NP_OF_TORCH = {torch.float64: np.float64, torch.int64: np.int64, torch.int32: np.int32, torch.uint8: np.uint8}
+
+
+class HostStager:
+    """Persistent pinned staging ring for pageable host arrays.
+
+    A pageable array cannot be read by the copy engine; `tensor.pin_memory()` per call costs a `cudaHostAlloc` of the
+    whole array (hundreds of ms per GB) plus a single-threaded memcpy.  Here NSLOT pinned slots are allocated once per
+    engine; an upload walks the array in slot-sized chunks: a few host threads copy chunk c into a free slot (numpy
+    releases the GIL for plain copies) while the DMA of chunk c-1 is still on the wire, then the H2D of the slot is
+    queued on the CURRENT stream (so the kernels that follow need no extra synchronisation) and an event marks the
+    slot reusable."""
+    SMALL = 1 << 20            # below this a plain copy is cheaper than the ring
+    SLOT_BYTES = 32 << 20
+    NSLOT = 4
+
+    def __init__(self, device):
+        self.device = device
+        self.slots = [torch.empty(self.SLOT_BYTES, dtype=torch.uint8).pin_memory() for _ in range(self.NSLOT)]
+        self.events = [None] * self.NSLOT
+        self.next = 0
+        nthr = max(1, min(8, (os.cpu_count() or 2) // 2))
+        self.pool = ThreadPoolExecutor(max_workers=nthr)
+        self.nthr = nthr
+
+    def _fill(self, dst_np, src_np):
+        n = src_np.shape[0]
+        if n < (4 << 20) or self.nthr == 1:
+            np.copyto(dst_np[:n], src_np)
+            return
+        step = -(-n // self.nthr)
+        futs = [self.pool.submit(np.copyto, dst_np[o:min(n, o + step)], src_np[o:min(n, o + step)])
+                for o in range(0, n, step)]
+        for f in futs:
+            f.result()
+
+    def upload(self, a, dtype):
+        out = torch.empty(a.shape, dtype=dtype, device=self.device)
+        src = a.reshape(-1).view(np.uint8)
+        dst = out.view(-1).view(torch.uint8)
+        stream = torch.cuda.current_stream(self.device)
+        for off in range(0, src.shape[0], self.SLOT_BYTES):
+            n = min(self.SLOT_BYTES, src.shape[0] - off)
+            i = self.next
+            self.next = (i + 1) % self.NSLOT
+            if self.events[i] is not None:
+                self.events[i].synchronize()
+            self._fill(self.slots[i].numpy(), src[off:off + n])
+            dst[off:off + n].copy_(self.slots[i][:n], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            self.events[i] = ev
+        return out
+
+
 class Engine:
     """One engine per process / GPU (one process per GPU under torchrun)."""
 
@@ -71,6 +128,7 @@ class Engine:
         _cabi.check("fsb_sm_count", self.lib.fsb_sm_count(self._h, ctypes.byref(n)))
         self.sm_count = n.value
         self._ws = {}
+        self._stager = None
         self.launch_count = 0
 
     def __del__(self):
@@ -97,21 +155,27 @@ class Engine:
         return torch.cuda.mem_get_info(self.device)
 
     def to_device(self, arr, dtype=torch.float64, non_blocking=True):
-        """Host numpy -> device tensor through pinned memory (or pass a device tensor through)."""
+        """Host numpy -> device tensor (or pass a device tensor through).  Pinned sources go straight onto the copy
+        engine; pageable sources (the ordinary numpy arrays a FitSNAP user passes to `perform_fit(a=, b=, w=)`) are
+        staged through this engine's persistent pinned ring (`HostStager`) -- no per-call `cudaHostAlloc`."""
         if isinstance(arr, torch.Tensor):
-            return arr.to(device=self.device, dtype=dtype)
+            if arr.device.type == "cuda":
+                return arr.to(device=self.device, dtype=dtype)
+            arr = arr.numpy()
         a = np.ascontiguousarray(arr)
+        want = _NP_OF_TORCH[dtype]
+        if a.dtype != want:
+            a = a.astype(want)
         t = torch.from_numpy(a)
-        if t.dtype != dtype:
-            t = t.to(dtype)
-        if not t.is_pinned():
-            # one staging copy into pinned memory; callers that care (bench e2e, the calculator
-            # plugin) hand in arrays that already live in pinned memory and skip it
-            try:
-                t = t.pin_memory()
-            except RuntimeError:
-                pass
-        return t.to(self.device, non_blocking=non_blocking)
+        if a.nbytes == 0:
+            return torch.empty(a.shape, dtype=dtype, device=self.device)
+        if t.is_pinned():
+            return t.to(self.device, non_blocking=non_blocking)
+        if a.nbytes < HostStager.SMALL:
+            return t.to(self.device)
+        if self._stager is None:
+            self._stager = HostStager(self.device)
+        return self._stager.upload(a, dtype)
 
     @staticmethod
     def _check_matrix(A, b, w, testing):
@@ -303,18 +367,26 @@ def fit_rows(engine, A, b, w, testing=None, alpha=0.0, refine=2, group=None, dia
                      launches=getattr(engine, "launch_count", 0) - start, extra={"factor": f})
 
 
-def fit_rows_min_norm(engine, A, b, w, testing, gaug, refine=3, group=None, rcond=None):
-    """Minimum-norm least squares for a rank-deficient system (what gelsd returns, svd.py:54):
-    x0 = G^+ c, then x += G^+ aw^T (bw - aw x) with the residual streamed from A.  `gaug` is the
-    (already all-reduced) augmented Gram of `fit_rows`."""
+def fit_rows_min_norm(engine, A, b, w, testing, gaug, refine=3, group=None, rcond=None, alpha=0.0):
+    """Eigenvalue-truncated solve for a numerically rank-deficient system.  alpha = 0: the minimum-norm least-squares
+    solution (what gelsd returns, svd.py:54): x0 = G^+ c, then x += G^+ aw^T (bw - aw x).  alpha > 0: the ridge
+    solution through (G + alpha I)^+ (sklearn's Ridge falls back to an SVD-based solve when its Cholesky breaks
+    down), refinement rhs aw^T (bw - aw x) - alpha x.  The residual is streamed from A; `gaug` is the (already
+    all-reduced) augmented Gram of `fit_rows`."""
     start = getattr(engine, "launch_count", 0)
     k = gaug.shape[0] - 1
-    pf = engine.pinv_factor(gaug, rcond)
+    gsolve = gaug
+    if alpha:
+        gsolve = gaug.clone()
+        gsolve.diagonal()[:k].add_(float(alpha))
+    pf = engine.pinv_factor(gsolve, rcond)
     x = engine.pinv_apply(pf, gaug[:, k], rhs_stride=k + 1)
     last = None
     for _ in range(int(refine)):
         g = engine.residual(A, b, w, testing, x)
         _all_reduce(g, group)
+        if alpha:
+            g = g - float(alpha) * x
         x_new = engine.pinv_apply(pf, g, x_in=x)
         last = (x_new - x).abs().max() / x_new.abs().max().clamp_min(1e-300)
         x = x_new
@@ -337,8 +409,24 @@ def refine_rows(engine, A, b, w, testing, res, group=None):
 _default_engine = None
 
 
+def local_device_index():
+    """GPU of this process: the node-local rank the launcher exported (torchrun LOCAL_RANK, Open MPI / MVAPICH /
+    Intel MPI / Slurm equivalents) modulo the device count -- so the ranks of one node spread over its GPUs the way the
+    reference's ranks spread over a node's cores (parallel_tools.py:262-300) -- else the current device."""
+    n = torch.cuda.device_count()
+    for var in ("LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID",
+                "SLURM_LOCALID"):
+        v = os.environ.get(var)
+        if v is not None and n > 0:
+            try:
+                return int(v) % n
+            except ValueError:
+                pass
+    return torch.cuda.current_device()
+
+
 def default_engine():
     global _default_engine
     if _default_engine is None:
-        _default_engine = Engine()
+        _default_engine = Engine(local_device_index())
     return _default_engine

@@ -19,16 +19,16 @@ def encode_groups(fs_dict, n_rows):
     testing = fs_dict["Testing"]
     rtype = fs_dict["Row_Type"]
     assert len(groups) == len(testing) == len(rtype) == n_rows
-    lut, keys = {}, []
-    gid = np.empty(n_rows, dtype=np.int32)
-    for i in range(n_rows):
-        key = (groups[i], bool(testing[i]), rtype[i])
-        j = lut.get(key)
-        if j is None:
-            j = lut[key] = len(keys)
-            keys.append(key)
-        gid[i] = j
-    return gid, keys
+    import pandas as pd
+    if n_rows == 0:
+        return np.zeros(0, dtype=np.int32), []
+    gc, gu = pd.factorize(np.asarray(groups, dtype=object))
+    rc, ru = pd.factorize(np.asarray(rtype, dtype=object))
+    tc = np.asarray(testing, dtype=bool).astype(np.int64)
+    code = (gc.astype(np.int64) * 2 + tc) * len(ru) + rc
+    uniq, gid = np.unique(code, return_inverse=True)
+    keys = [(gu[u // (2 * len(ru))], bool((u // len(ru)) % 2), ru[u % len(ru)]) for u in uniq]
+    return gid.astype(np.int32), keys
 
 
 def metrics_from_sums(s):
@@ -69,13 +69,61 @@ def errors_frame(stats, keys):
     return df
 
 
-def linear_error_analysis(engine, A, b, w, fs_dict, x):
-    """Device pass + host formatting.  A, b, w, x: device tensors (or host arrays: uploaded)."""
+def _global_keys(keys, group):
+    """Union of the (group, test, row type) keys of all ranks, in one order on every rank."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, keys, group=group)
+    seen, out = set(), []
+    for lst in gathered:
+        for key in lst:
+            if key not in seen:
+                seen.add(key)
+                out.append(key)
+    return sorted(out)
+
+
+def linear_error_analysis(engine, A, b, w, fs_dict, x, group=None):
+    """Device pass + host formatting.  A, b, w, x: device tensors (or host arrays: uploaded).  With `group` (row-sharded
+    fit, one shard per rank) the keys are unified across ranks, the per-group sums all-reduced, and every rank ends
+    with the table of the whole data set."""
     import torch
     A = engine.to_device(A)
     b = engine.to_device(b).reshape(-1)
     w = engine.to_device(w).reshape(-1)
     x = engine.to_device(np.asarray(x, dtype=np.float64).reshape(-1)) if not isinstance(x, torch.Tensor) else x
     gid, keys = encode_groups(fs_dict, A.shape[0])
+    sharded = False
+    if group is not None:
+        import torch.distributed as dist
+        sharded = dist.is_initialized() and dist.get_world_size(group) > 1
+    if sharded:
+        all_keys = _global_keys(keys, group)
+        pos = {key: i for i, key in enumerate(all_keys)}
+        gid = np.asarray([pos[key] for key in keys], dtype=np.int32)[gid] if len(keys) else gid
+        keys = all_keys
     stats = engine.group_stats(A, b, w, engine.to_device(gid, dtype=torch.int32), x, len(keys))
+    if sharded:
+        import torch.distributed as dist
+        dist.all_reduce(stats, group=group)
     return errors_frame(stats.cpu().numpy(), keys)
+
+
+def light_frame(engine, A, b, w, fs_dict, x):
+    """The frame of solver.py:374-382 without its K descriptor columns: truths, preds (= a @ fit from the device),
+    weights and every per-row list of `fs_dict`."""
+    import pandas as pd
+    import torch
+    n = A.shape[0]
+    to_host = lambda v: v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+    df = pd.DataFrame({"truths": to_host(b).reshape(-1)})
+    if x is not None:
+        Ad = engine.to_device(A)
+        xd = engine.to_device(np.asarray(x, dtype=np.float64).reshape(-1))
+        df["preds"] = engine.predict(Ad, xd).cpu().numpy()
+    df["weights"] = to_host(w).reshape(-1)
+    for key, val in (fs_dict or {}).items():
+        if isinstance(val, list) and len(val) == n:
+            df[key] = val
+    return df

@@ -39,7 +39,7 @@ def register(engine=None):
             mirror.__init__(self, name_, pt, config)
             self.engine = engine
         return type(name, (mirror, Solver), {"__init__": __init__, "__doc__": mirror.__doc__,
-                                             "__module__": __name__})
+                                             "__module__": __name__, "_offset": Solver._offset})
 
     def calculator_class(name, mixin, ref):
         def __init__(self, name_, pt, config):
@@ -48,11 +48,20 @@ def register(engine=None):
             self.pt.check_lammps()
             self._b200_engine = engine
         body = {"__init__": __init__, "__doc__": mixin.__doc__, "__module__": __name__}
-        # LAMMPS set-up (descriptor evaluation side) stays the reference's own code
-        for meth in ("get_width", "_prepare_lammps", "_set_box", "_create_atoms", "_set_computes",
-                     "_create_spins", "_create_charge"):
-            if meth in ref.__dict__:
-                body[meth] = ref.__dict__[meth]
+        # Everything the stock class defines stays the reference's own code, executed unmodified: the LAMMPS
+        # set-up (descriptor evaluation side: get_width, _prepare_lammps, _set_box, _create_atoms, _set_computes,
+        # _create_spins, _create_charge, _set_variables) and the nonlinear / preprocessing collectors
+        # (_collect_lammps_nonlinear, _collect_lammps_preprocess -- the network solvers' path, fitsnap.py:161-178).
+        # Only the two linear collectors are replaced by the mixin; the stock versions are kept under `_ref_*`
+        # for the layouts the batched scatter does not cover (bikflag, dgradflag, per_atom_energy).
+        replaced = ("__init__", "_collect_lammps", "_collect_lammps_single")
+        for meth, fn in ref.__dict__.items():
+            if meth.startswith("__") and meth.endswith("__"):
+                continue
+            if meth in replaced:
+                body["_ref_" + meth.lstrip("_")] = fn
+            else:
+                body[meth] = fn
         return type(name, (mixin, LammpsBase), body)
 
     _registered["SVD"] = solver_class("SVD", bs.SVD)

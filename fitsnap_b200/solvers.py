@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import engine as _engine
+from .hostmirror import LazyHostMirror, shared_shape
 
 
 def _section(config, name):
@@ -83,17 +84,27 @@ class LinearSolverBase:
             raise ValueError("Testing mask has %d entries for %d rows" % (testing.shape[0], n))
         return testing if testing.any() else None
 
+    def _shared_rows(self):
+        """a, b, w when `perform_fit()` / `error_analysis()` are called without arrays (svd.py:42-44): the rows the
+        drop-in calculator left on the device, unless the host copy of an array has been handed out since
+        (`LazyHostMirror.exposed`: it may have been edited in place, e.g. bayesian_active_learning.py rescales `w`)
+        -- that array is then re-read from the host.  Arrays filled by the stock calculator are host arrays."""
+        sa = self.pt.shared_arrays
+        dev = getattr(self.pt, "fitsnap_b200_device", None)
+        sharded = self.process_group is not None
+        out = []
+        for name, key in (("a", "A"), ("b", "b"), ("w", "w")):
+            m = sa[name]
+            if (dev is not None and isinstance(m, LazyHostMirror) and not m.exposed and
+                    (sharded or (dev["first_row"] == 0 and dev["n_rows"] == shared_shape(m)[0]))):
+                out.append(dev[key])
+            else:
+                out.append(m.array)
+        return out
+
     def _resolve_inputs(self, a, b, w, fs_dict, trainall):
         if a is None and b is None and w is None:          # svd.py:42-44
-            dev = getattr(self.pt, "fitsnap_b200_device", None)
-            nb = self.pt.shared_arrays["b"].array.shape[0]
-            if dev is not None and dev["first_row"] == 0 and dev["n_rows"] == nb:
-                # rows assembled by the drop-in calculator are still resident on the device
-                a, b, w = dev["A"], dev["b"], dev["w"]
-            else:
-                a = self.pt.shared_arrays["a"].array
-                b = self.pt.shared_arrays["b"].array
-                w = self.pt.shared_arrays["w"].array
+            a, b, w = self._shared_rows()
         if a is None or b is None or w is None:
             raise ValueError("a, b and w must be given together")
         n = a.shape[0]
@@ -127,8 +138,10 @@ class LinearSolverBase:
             while last > 1e-14 and rounds < self.max_refine:
                 res2 = _engine.refine_rows(eng, A, B, W, T, res, group=self.process_group)
                 new = float(res2.last_correction)
-                res = res2
                 rounds += 1
+                if not (new <= last):       # the correction grew (or is NaN): keep the previous iterate
+                    break
+                res = res2
                 if new > 0.5 * last:        # stalled at the attainable accuracy
                     break
                 last = new
@@ -149,31 +162,110 @@ class LinearSolverBase:
         res = self._run_fit(A, B, W, T, self._alpha())
         self.last_result = res
         self._check_info(res)
-        if self.info["status"] != 0 and self._alpha() == 0.0 and self.min_norm_fallback:
-            # linearly dependent columns: lstsq (svd.py:54) returns the minimum-norm solution
-            res = _engine.fit_rows_min_norm(self._engine(), A, B, W, T, res.gaug, refine=3, group=self.process_group)
-            self.last_result = res
-            self.info["min_norm_rank"] = int(res.info[0].item())
+        if self.info["status"] != 0:
+            res = self._rank_deficient(A, B, W, T, res)
         self.fit = res.coefficients()
 
+    def _warn(self, msg):
+        pr = getattr(self.pt, "single_print", None)
+        (pr if pr is not None else print)(msg)
+
+    def _rank_deficient(self, A, B, W, T, res):
+        """The equilibrated Cholesky met a pivot below 64 k eps: the weighted design matrix has numerically
+        dependent columns.  What the reference does then: `lstsq(aw, bw, 1e-13)` (svd.py:54) returns the
+        minimum-norm solution, sklearn's Ridge falls back from Cholesky to an SVD-based solve of the same
+        ridge problem.  Both are reproduced through the eigendecomposition of the Gram (`fsb_pinv_factor` on
+        G + alpha I, refinement against A) and the user is told: the truncation acts on eigenvalues of
+        G, i.e. singular values of aw below ~sqrt(k eps) sigma_max ~ 1e-7 sigma_max are cut, where gelsd cuts at
+        1e-13 sigma_max."""
+        alpha = self._alpha()
+        k = res.gaug.shape[0] - 1
+        self._warn("! WARNING (fitsnap_b200): %s: the weighted design matrix is numerically rank deficient (first "
+                   "dependent column %d, %d dropped by the Cholesky factor); switching to the eigenvalue-truncated "
+                   "%s solve of the Gram (singular values below ~%.0e sigma_max are cut; scipy's gelsd cuts at 1e-13)"
+                   % (self.name, self.info["first_bad_column"], self.info["deficient"],
+                      "minimum-norm" if alpha == 0.0 else "ridge", float(np.sqrt(k * 2.220446049250313e-16))))
+        if not self.min_norm_fallback:
+            return res
+        res2 = _engine.fit_rows_min_norm(self._engine(), A, B, W, T, res.gaug, refine=3, group=self.process_group,
+                                         alpha=alpha)
+        self.last_result = res2
+        self.info["min_norm_rank"] = int(res2.info[0].item())
+        return res2
+
+    # -- error analysis (SURVEY 8f row 1) ---------------------------------------------------
+    def error_analysis(self, a=None, b=None, w=None, fs_dict=None):
+        """Drop-in for the linear tail of `Solver.error_analysis` (solver.py:137-435, linear branch :368-435):
+        `self.errors` gets the same (Group, Weighting, Testing, Subsystem) x (ncount, mae, rmse, rsq) table, and
+        `_offset()` is applied for SNAP with bzeroflag (:432-435) -- but `preds = a @ fit` and the per-group sums come
+        from ONE device pass over A (`fsb_group_stats`) instead of `DataFrame(a)` + groupby over every row and
+        column.  `self.df` is built on demand and holds truths / preds / weights and the per-row lists (not the K
+        descriptor columns).  When the frame itself is an output product (`[EXTRAS] dump_dataframe`) or the solver is
+        not linear, the reference's implementation runs unchanged."""
+        if not self.linear or _get(_section(self.config, "EXTRAS"), "dump_dataframe", False):
+            return super().error_analysis(a=a, b=b, w=w, fs_dict=fs_dict)
+        self.errors = []
+        sharded = self.process_group is not None
+        if getattr(self.pt, "_rank", 0) != 0 and not sharded:          # solver.py:160
+            return
+        if a is None and b is None and w is None and fs_dict is None:   # solver.py:368-372
+            a, b, w = self._shared_rows()
+            fs_dict = self.pt.fitsnap_dict
+        fit0 = None if self.fit is None else np.array(self.fit, dtype=np.float64).reshape(-1)   # before _offset
+        self._df, self._df_inputs = None, (a, b, w, fs_dict, fit0)
+        true_multinode = bool(_get(_section(self.config, "SOLVER"), "true_multinode", False))
+        if self.fit is not None and not true_multinode:
+            from . import errors as _errors
+            fit = np.asarray(self.fit, dtype=np.float64).reshape(-1)
+            self.errors = _errors.linear_error_analysis(self._engine(), a, b, w, fs_dict, fit, group=self.process_group)
+        if self.fit is not None:
+            calc = _section(self.config, "CALCULATOR")
+            bis = _section(self.config, "BISPECTRUM")
+            if _get(calc, "calculator", None) == "LAMMPSSNAP" and _get(bis, "bzeroflag", False):
+                self._offset()
+
     def error_analysis_device(self, a=None, b=None, w=None, fs_dict=None):
-        """Linear error analysis (solver.py:368-429) from device-side sums: fills `self.errors` with
-        the same table the reference builds through a full pandas frame.  `self.fit` must be set.
-        Inputs default to pt.shared_arrays / pt.fitsnap_dict like the reference's error_analysis."""
+        """The device pass alone (no `_offset`, no frame): returns and stores the errors table."""
         from . import errors as _errors
         if a is None and b is None and w is None and fs_dict is None:
-            dev = getattr(self.pt, "fitsnap_b200_device", None)
-            nb = self.pt.shared_arrays["b"].array.shape[0]
-            if dev is not None and dev["first_row"] == 0 and dev["n_rows"] == nb:
-                a, b, w = dev["A"], dev["b"], dev["w"]
-            else:
-                a = self.pt.shared_arrays["a"].array
-                b = self.pt.shared_arrays["b"].array
-                w = self.pt.shared_arrays["w"].array
+            a, b, w = self._shared_rows()
             fs_dict = self.pt.fitsnap_dict
         fit = np.asarray(self.fit, dtype=np.float64).reshape(-1)
-        self.errors = _errors.linear_error_analysis(self._engine(), a, b, w, fs_dict, fit)
+        self.errors = _errors.linear_error_analysis(self._engine(), a, b, w, fs_dict, fit, group=self.process_group)
         return self.errors
+
+    @property
+    def df(self):
+        """solver.py:374-382 frame, built on first access: truths, preds, weights + the per-row lists."""
+        if getattr(self, "_df", None) is None and getattr(self, "_df_inputs", None) is not None:
+            from . import errors as _errors
+            a, b, w, fs_dict, fit = self._df_inputs
+            self._df = _errors.light_frame(self._engine(), a, b, w, fs_dict, fit)
+        return getattr(self, "_df", None)
+
+    @df.setter
+    def df(self, value):
+        self._df, self._df_inputs = value, None
+
+    def _offset(self):
+        """solver.py:78-102 restated for stand-alone use of this mirror (no fitsnap3lib on the path): one zero
+        coefficient in front of every type's block when bzeroflag = 1.  The classes built by plugin.register() take
+        the reference's own `Solver._offset` instead."""
+        nt = int(_get(_section(self.config, "BISPECTRUM"), "numtypes", 1))
+        nc = int(_get(_section(self.config, "BISPECTRUM"), "ncoeff", 0))
+        if nt > 1:
+            fit = np.asarray(self.fit).reshape(nt, nc)
+            self.fit = np.concatenate([np.zeros((nt, 1)), fit], axis=1).reshape((-1, 1))
+        else:
+            self.fit = np.insert(self.fit, 0, 0)
+        fs = getattr(self, "fit_sam", None)
+        if fs is not None:
+            if nt > 1:
+                nsam = fs.shape[0]
+                fs3 = fs.reshape(nsam, nt, nc)
+                self.fit_sam = np.concatenate([np.zeros((nsam, nt, 1)), fs3], axis=2).reshape(nsam, -1) + 0.0
+            else:
+                self.fit_sam = np.insert(fs, 0, 0, axis=1)
 
     def _check_info(self, res):
         info = res.info_host()

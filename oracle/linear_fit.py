@@ -111,6 +111,125 @@ def assemble(configs, numtypes, ncoeff, bzeroflag, blank2j,
             np.concatenate([p[2] for p in parts]))
 
 
+def config_rows_single(block, natoms, volume, energy, forces, stress, eweight, fweight, vweight,
+                       type_fraction, numtypes, ncoeff, bzeroflag, blank2j,
+                       use_energy=True, use_force=True, use_stress=True):
+    """(a, b, w) of `process_single` for ONE configuration: lammps_snap.py:224-389 /
+    lammps_pace.py:197-366 (`_collect_lammps_single`, bikflag = 0).  Same row arithmetic as
+    `config_rows`, different layout: `a` always holds the energy row and the 3N force rows
+    (+ the 6 virial rows iff `use_stress`: `na = rows of the block, minus 6 without stress`,
+    :266-269), `irow` advances past a family whether or not it is assembled (:341, :364), so
+    the rows of a switched-off family stay zero; weights default to 1.0 when the data
+    dictionary has no eweight / fweight / vweight key (:337, :360, :383) -- pass None."""
+    n = int(natoms)
+    k = descriptor_width(ncoeff, numtypes, bzeroflag)
+    na = 1 + 3 * n + (6 if use_stress else 0)
+    a, b, w = np.zeros((na, k)), np.zeros(na), np.zeros(na)
+    ew, fw, vw = (1.0 if v is None else v for v in (eweight, fweight, vweight))
+    for on, dst0, cnt, sel in ((use_energy, 0, 1, (True, False, False)), (use_force, 1, 3 * n, (False, True, False)),
+                               (use_stress, 1 + 3 * n, 6, (False, False, True))):
+        if on:
+            ra, rb, rw = config_rows(block, natoms, volume, energy, forces, stress, ew, fw, vw, type_fraction,
+                                     numtypes, ncoeff, bzeroflag, blank2j, *sel)
+            a[dst0:dst0 + cnt], b[dst0:dst0 + cnt], w[dst0:dst0 + cnt] = ra, rb, rw
+    return a, b, w
+
+
+# ------------------------------------------------- the reference's CPU path, step for step
+# Used by bench.py's reference arm / cpu_baseline: the functions above restate WHAT the reference
+# computes; these two also do it HOW the reference does it (the numpy calls that dominate its
+# time), so that timing them is timing the reference's algorithm, not a tidied-up version.
+def config_rows_as_reference(block, natoms, volume, energy, forces, stress, eweight, fweight, vweight,
+                             type_fraction, numtypes, ncoeff, bzeroflag, blank2j, out_a, out_b, out_w, index):
+    """lammps_snap.py:430-549 with its own operations: in-place `/= num_atoms` on the block view (:435),
+    `np.concatenate` of the one-hot / zero lead columns (:457-464, :495-499, :528-532), the force and
+    virial rows multiplied by the DENSE `np.diag(blank2J)` with `np.matmul` (:501-502, :535-536: an
+    O(rows K^2) product for a column mask), rows written into the shared arrays at `index`.
+    Returns the next index.  Bit-identical to `config_rows` (asserted in tests/test_oracle.py)."""
+    n = int(natoms)
+    kraw = ncoeff * numtypes
+    k = descriptor_width(ncoeff, numtypes, bzeroflag)
+    lmp = np.array(block, dtype=np.float64)          # the LAMMPS array of this configuration (:423)
+    if np.isinf(lmp).any() or np.isnan(lmp).any():   # :426-428
+        raise ValueError("Nan in computed data")
+    irow = 0
+    b_sum = lmp[irow:irow + 1, :kraw]
+    b_sum /= n                                       # :435
+    if not bzeroflag:                                # :455-464
+        b_sum = b_sum.reshape(numtypes, ncoeff)
+        onehot = np.asarray(type_fraction, dtype=np.float64).reshape(numtypes, 1)
+        b_sum = np.concatenate((onehot, b_sum), axis=1).reshape(k)
+    out_a[index:index + 1] = b_sum * blank2j[np.newaxis, :]          # :466-467
+    out_b[index] = (energy - lmp[irow, kraw]) / n                    # :469-473
+    out_w[index] = eweight
+    index += 1
+    irow += 1
+    nf = 3 * n
+    db = lmp[irow:irow + nf, :kraw]
+    if not bzeroflag:                                # :495-499
+        db = db.reshape(nf, numtypes, ncoeff)
+        db = np.concatenate([np.zeros((nf, numtypes, 1)), db], axis=2).reshape(nf, k)
+    out_a[index:index + nf] = np.matmul(db, np.diag(blank2j))        # :501-502
+    out_b[index:index + nf] = np.asarray(forces, dtype=np.float64).ravel() - lmp[irow:irow + nf, kraw]
+    out_w[index:index + nf] = fweight
+    index += nf
+    irow += nf
+    vb = VIRIAL_UNIT * lmp[irow:irow + 6, :kraw] / volume             # :526
+    if not bzeroflag:
+        vb = vb.reshape(6, numtypes, ncoeff)
+        vb = np.concatenate([np.zeros((6, numtypes, 1)), vb], axis=2).reshape(6, k)
+    out_a[index:index + 6] = np.matmul(vb, np.diag(blank2j))         # :535-536
+    s = np.asarray(stress, dtype=np.float64)
+    out_b[index:index + 6] = s[list(VOIGT_I), list(VOIGT_J)].ravel() - lmp[irow:irow + 6, kraw]
+    out_w[index:index + 6] = vweight
+    return index + 6
+
+
+def assemble_as_reference(configs, numtypes, ncoeff, bzeroflag, blank2j):
+    """calculator.py:287-291 (allocate the shared a, b, w) + one `_collect_lammps` per configuration, all three
+    row families on (the bench workloads)."""
+    k = descriptor_width(ncoeff, numtypes, bzeroflag)
+    n_rows = sum(rows_per_config(c["natoms"]) for c in configs)
+    a, b, w = np.zeros((n_rows, k)), np.zeros(n_rows), np.zeros(n_rows)
+    blank2j = np.asarray(blank2j, dtype=np.float64)
+    index = 0
+    for c in configs:
+        index = config_rows_as_reference(c["block"], c["natoms"], c["volume"], c["energy"], c["forces"], c["stress"],
+                                         c["eweight"], c["fweight"], c["vweight"], c.get("type_fraction"),
+                                         numtypes, ncoeff, bzeroflag, blank2j, a, b, w, index)
+    return a, b, w
+
+
+def ridge_perform_fit_as_reference(a, b, w, alpha, testing=None):
+    """ridge.py:24-60 step for step: the training mask as a PYTHON LIST of bools (:28-33 -- numpy turns the
+    list into an index array on every one of the three fancy-indexing copies), `w[:, None] * a[training]`
+    (a second full copy of A, :39), sklearn Ridge (:49-57) and the residual product `aw @ coef - bw` (:60)."""
+    from sklearn.linear_model import Ridge
+    if testing is not None:
+        training = [not elem for elem in testing]
+    else:
+        training = [True] * np.shape(a)[0]
+    w = w[training]                 # ridge.py:36 (the shared-array branch; the explicit-array branch :39 forgets this
+    aw, bw = w[:, np.newaxis] * a[training], w * b[training]      # mask and only works when nothing is masked)
+    reg = Ridge(alpha=alpha, fit_intercept=False)
+    reg.fit(aw, bw)
+    residues = np.matmul(aw, reg.coef_) - bw
+    return reg.coef_, residues
+
+
+def svd_perform_fit_as_reference(a, b, w, testing=None):
+    """svd.py:31-54 step for step (list mask, two copies of A, scipy.linalg.lstsq(aw, bw, 1e-13))."""
+    from scipy.linalg import lstsq
+    if testing is not None:
+        training = [not elem for elem in testing]
+    else:
+        training = [True] * np.shape(a)[0]
+    w = w[training]                 # svd.py:43
+    aw, bw = w[:, np.newaxis] * a[training], w * b[training]
+    fit, _residues, _rank, _s = lstsq(aw, bw, 1.0e-13)
+    return fit
+
+
 # ------------------------------------------------------------------------ solvers
 def weighted_system(a, b, w, testing=None):
     """svd.py:35-46 / ridge.py:28-39: boolean-mask the training rows, then

@@ -12,6 +12,9 @@ Fixtures
                       LASSO results on that triple (reference classes, this container).
   scatter_*.npz       synthetic raw LAMMPS blocks + the (A, b, w, Testing) the unmodified
                       LammpsSnap / LammpsPace calculators assemble from them.
+  single_*.npz        the same kind of blocks through `process_single` (lammps_base.py:101-125): per-configuration
+                      (a, b, w) of the unmodified `_collect_lammps_single`, incl. switched-off row families (zero rows)
+                      and missing weight keys (default 1.0).
   solve_*.npz         reference SVD / RIDGE fits of the seeded synthetic systems of
                       tests/synth.py (well- and ill-conditioned, zero columns, k > 128);
                       the systems themselves are regenerated from the seed at test time.
@@ -153,13 +156,88 @@ def save_scatter(tag, cfgs, blocks, vols, a, b, w, lists, ncoeff, numtypes, bzer
     print("scatter_%s" % tag, a.shape, "zero cols:", int((b2j == 0).sum()))
 
 
+def single_cases():
+    """`process_single` outputs of the unmodified reference (lammps_snap.py:224-389, lammps_pace.py:197-366)."""
+    rng = np.random.default_rng(99)
+    names = ["In", "P"]
+    snap = [
+        ("snap_b0_efs", dict(bzeroflag=0, twojmax="6 6", energy=1, force=1, stress=1), False),
+        ("snap_b1_ef", dict(bzeroflag=1, twojmax="6 4", energy=1, force=1, stress=0), False),
+        ("snap_b0_es", dict(bzeroflag=0, twojmax="4 4", energy=1, force=0, stress=1), False),
+        ("snap_b1_fs", dict(bzeroflag=1, twojmax="4 4", energy=0, force=1, stress=1), True),
+    ]
+    for tag, kw, drop in snap:
+        pt, cfg = rd.make_reference_context(numtypes=2, types="In P", **kw)
+        sec = cfg.sections["BISPECTRUM"]
+        nc, b2j, tm = sec.ncoeff, np.array(sec.blank2J, dtype=np.float64), sec.type_mapping
+        cfgs, blocks, vols = _single_inputs(rng, nc, 2, names, 7)
+        out, _ = rd.ref_single(cfgs, blocks, vols, numtypes=2, types="In P", drop_weights=drop, **kw)
+        save_single(tag, cfgs, blocks, vols, out, nc, 2, kw["bzeroflag"], b2j, tm, kw, drop)
+    nc, nt = 23, 2
+    for tag, bz in (("pace_b0_efs", 0), ("pace_b1_ef", 1)):
+        k = nc * nt + (0 if bz else nt)
+        b2j = np.ones(k)
+        b2j[rng.choice(k, 3, replace=False)] = 0.0
+        tm = {"In": 1, "P": 2}
+        ace = dict(numtypes=nt, ncoeff=nc, bzeroflag=bz, bikflag=0, dgradflag=0, blank2J=b2j, type_mapping=tm,
+                   rcutfac=[4.0])
+        kw = dict(bzeroflag=bz, twojmax="6 6", energy=1, force=1, stress=0 if bz else 1)
+        cfgs, blocks, vols = _single_inputs(rng, nc, nt, names, 6)
+        out, _ = rd.ref_single(cfgs, blocks, vols, calculator="LAMMPSPACE", ace=ace, numtypes=nt, types="In P", **kw)
+        save_single(tag, cfgs, blocks, vols, out, nc, nt, bz, b2j, tm, kw, False)
+
+
+def _single_inputs(rng, nc, nt, names, ncfg):
+    cfgs, blocks, vols = [], [], []
+    for i in range(ncfg):
+        n = int(rng.integers(1, 11))
+        cfgs.append(rd.make_config_dict(n, nt, rng, names, group="s%d" % (i % 2), fname="one%d" % i,
+                                        eweight=float(10 ** rng.uniform(-2, 2)), fweight=float(10 ** rng.uniform(-2, 2)),
+                                        vweight=float(10 ** rng.uniform(-9, -5))))
+        blocks.append(rng.standard_normal((1 + 3 * n + 6, nc * nt + 1)) * 10.0 ** rng.uniform(-3, 3, (1, nc * nt + 1)))
+        vols.append(float(rng.uniform(20, 4000)))
+    return cfgs, blocks, vols
+
+
+def save_single(tag, cfgs, blocks, vols, out, ncoeff, numtypes, bzeroflag, b2j, tm, kw, drop):
+    natoms = np.array([c["NumAtoms"] for c in cfgs], dtype=np.int32)
+    tf = np.zeros((len(cfgs), numtypes))
+    for i, c in enumerate(cfgs):
+        for at in c["AtomTypes"]:
+            tf[i, tm[at] - 1] += 1
+        tf[i] /= len(c["AtomTypes"])
+    np.savez_compressed(
+        os.path.join(OUT, "single_%s.npz" % tag),
+        raw=np.concatenate(blocks, 0), natoms=natoms, volume=np.array(vols),
+        energy=np.array([c["Energy"] for c in cfgs]),
+        forces=np.concatenate([c["Forces"].reshape(-1) for c in cfgs]),
+        stress=np.stack([c["Stress"] for c in cfgs]),
+        atom_type_index=np.concatenate([[tm[a] for a in c["AtomTypes"]] for c in cfgs]).astype(np.int32),
+        eweight=np.array([c["eweight"] for c in cfgs]), fweight=np.array([c["fweight"] for c in cfgs]),
+        vweight=np.array([c["vweight"] for c in cfgs]), weights_dropped=bool(drop), type_fraction=tf, blank2j=b2j,
+        ncoeff=ncoeff, numtypes=numtypes, bzeroflag=bzeroflag,
+        use_energy=kw["energy"], use_force=kw["force"], use_stress=kw["stress"],
+        rows_per_config=np.array([o[0].shape[0] for o in out], dtype=np.int64),
+        ref_a=np.concatenate([o[0] for o in out], 0), ref_b=np.concatenate([o[1] for o in out]),
+        ref_w=np.concatenate([o[2] for o in out]))
+    print("single_%s" % tag, [o[0].shape for o in out][:3])
+
+
 def main():
+    import sys
     os.makedirs(OUT, exist_ok=True)
     assert rd.reference_available(), "needs the reference tree at %s" % rd.REFERENCE_ROOT
-    ta_linear()
-    solve_cases()
-    anl_cases()
-    scatter_cases()
+    which = sys.argv[1:] or ["ta", "solve", "anl", "scatter", "single"]
+    if "ta" in which:
+        ta_linear()
+    if "solve" in which:
+        solve_cases()
+    if "anl" in which:
+        anl_cases()
+    if "scatter" in which:
+        scatter_cases()
+    if "single" in which:
+        single_cases()
 
 
 if __name__ == "__main__":

@@ -259,3 +259,37 @@ def ref_scatter(configs, blocks, volumes, calculator="LAMMPSSNAP", ace=None, use
     w = np.array(pt.shared_arrays["w"].array, dtype=np.float64)
     lists = {k: list(v) for k, v in pt.fitsnap_dict.items() if isinstance(v, list)}
     return a, b, w, lists, cfg, pt, calc
+
+
+def ref_single(configs, blocks, volumes, calculator="LAMMPSSNAP", ace=None, use_factory=False, context=None,
+               drop_weights=False, **ctx):
+    """Run `process_single` (lammps_base.py:101-125 -> `_collect_lammps_single`, lammps_snap.py:224-389 /
+    lammps_pace.py:197-366) of the unmodified reference calculator -- or, with `use_factory`, of whatever class the
+    reference's factory returns -- over synthetic compute blocks.  Returns a list of (a, b, w) per configuration and
+    the calculator.  `drop_weights` removes the eweight / fweight / vweight keys (they then default to 1.0)."""
+    pt, cfg = context if context is not None else make_reference_context(**ctx)
+    if calculator == "LAMMPSPACE":
+        cfg.sections["CALCULATOR"].calculator = "LAMMPSPACE"
+        cfg.sections["ACE"] = SimpleNamespace(**ace)
+    from fitsnap3lib.calculators.lammps_snap import LammpsSnap
+    from fitsnap3lib.calculators.lammps_pace import LammpsPace
+    if use_factory:
+        from fitsnap3lib.calculators.calculator_factory import calculator as make_calculator
+        calc = make_calculator(calculator, pt, cfg)
+    else:
+        cls = LammpsPace if calculator == "LAMMPSPACE" else LammpsSnap
+        calc = cls(calculator, pt, cfg)
+    calc._prepare_lammps = lambda: calc._set_structure()
+    if calculator == "LAMMPSPACE":
+        calc._set_box = lambda: calc._set_box_helper(numtypes=ace["numtypes"])
+    calc.shared_index = 0
+    calc.distributed_index = 0
+    out = []
+    for i, c in enumerate(configs):
+        if drop_weights:
+            c = {k_: v for k_, v in c.items() if k_ not in ("eweight", "fweight", "vweight")}
+        FakeLammps.staged_block = np.array(blocks[i], dtype=np.float64)    # the reference divides the block in place
+        FakeLammps.staged_volume = volumes[i]
+        a, b, w = calc.process_single(c, i)
+        out.append((np.array(a, dtype=np.float64), np.array(b, dtype=np.float64), np.array(w, dtype=np.float64)))
+    return out, calc

@@ -126,3 +126,73 @@ def test_shard_configs_by_rows_balances_rows():
         per = np.array([rows[bnd[i]:bnd[i + 1]].sum() for i in range(world)])
         assert per.sum() == rows.sum()
         assert per.max() - per.min() <= 2 * rows.max()
+
+
+def _plugin_worker(rank, world, port, out_dir):
+    """One FitSnap-style flow per rank through the REFERENCE's factories after plugin.register(): every rank assembles
+    its own share of the configurations, `distributed.attach` makes perform_fit / error_analysis row-sharded."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import ref_driver as rd
+    rd.install_fake_lammps()
+    from fitsnap_b200 import distributed, plugin
+    from tests.fake_engine import OracleEngine
+    eng = OracleEngine()
+    plugin.register(engine=eng)
+    from fitsnap3lib.solvers.solver_factory import solver
+    cfgs, blocks, vols, kw = _plugin_inputs()
+    bnd = shard_configs_by_rows([7 + 3 * c["NumAtoms"] for c in cfgs], world)
+    lo, hi = int(bnd[rank]), int(bnd[rank + 1])
+    a, b, w, lists, cfg, pt, calc = rd.ref_scatter(cfgs[lo:hi], blocks[lo:hi], vols[lo:hi], use_factory=True, **kw)
+    s = solver("SVD", pt, cfg)
+    s.refine = 2
+    distributed.attach(s, engine=eng)
+    s.perform_fit()
+    fit = s.fit.copy()
+    s.error_analysis()
+    s.errors.to_pickle(os.path.join(out_dir, "err_%d.pkl" % rank))
+    np.save(os.path.join(out_dir, "fit_%d.npy" % rank), fit)
+    dist.destroy_process_group()
+
+
+def _plugin_inputs():
+    from oracle import ref_driver as rd
+    rng = np.random.default_rng(17)
+    kw = dict(numtypes=1, types="Ta", twojmax="4", bzeroflag=0)
+    _pt, cfg0 = rd.make_reference_context(**kw)
+    nc = cfg0.sections["BISPECTRUM"].ncoeff
+    cfgs, blocks, vols = [], [], []
+    for i in range(60):
+        n = int(rng.integers(1, 9))
+        cfgs.append(rd.make_config_dict(n, 1, rng, ["Ta"], group="g%d" % (i % 3), fname="f%d" % i,
+                                        eweight=float(10 ** rng.uniform(-2, 2)), fweight=float(10 ** rng.uniform(-2, 2)),
+                                        vweight=float(10 ** rng.uniform(-9, -5)), test_bool=bool(i % 4 == 1)))
+        blocks.append(rng.standard_normal((1 + 3 * n + 6, nc + 1)))
+        vols.append(float(rng.uniform(20, 400)))
+    return cfgs, blocks, vols, kw
+
+
+def test_sharded_fit_through_the_reference_factories(tmp_path):
+    import pandas as pd
+    from oracle import ref_driver as rd
+    if not rd.reference_available():
+        pytest.skip("reference tree only exists in the build container")
+    world = 2
+    mp.spawn(_plugin_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    fits = [np.load(tmp_path / ("fit_%d.npy" % r)) for r in range(world)]
+    assert np.array_equal(fits[0], fits[1])
+    cfgs, blocks, vols, kw = _plugin_inputs()
+    a, b, w, lists, *_ = rd.ref_scatter(cfgs, blocks, vols, **kw)                     # stock classes, one process
+    x_ref, sref = rd.ref_fit("SVD", a, b, w, testing=np.array(lists["Testing"]))
+    assert lf.coeff_rel_err(fits[0], x_ref)[0] < 1e-9
+    sref.pt.fitsnap_dict.update({k_: v for k_, v in lists.items()})
+    sref.error_analysis()
+    errs = [pd.read_pickle(tmp_path / ("err_%d.pkl" % r)) for r in range(world)]
+    assert errs[0].equals(errs[1])
+    ref = sref.errors
+    assert list(errs[0].index) == list(ref.index)
+    assert np.array_equal(errs[0]["ncount"].values, ref["ncount"].values)
+    for col in ("mae", "rmse", "rsq"):
+        r, d = ref[col].values.astype(float), errs[0][col].values.astype(float)
+        ok = np.isclose(d, r, rtol=1e-7, atol=1e-12) | (np.isnan(d) & np.isnan(r)) | (~np.isfinite(r) & ~np.isfinite(d))
+        assert ok.all(), col

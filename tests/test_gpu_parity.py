@@ -409,17 +409,19 @@ def _pt(a, b, w, testing=None):
                            fitsnap_dict={"Testing": list(map(bool, testing)) if testing is not None else [False] * len(b)})
 
 
-def test_solver_mirror_svd_shared_arrays_and_explicit(ta):
+def test_solver_mirror_svd_shared_arrays_and_explicit(engine, ta):
     """`SVD.perform_fit()` with no arguments reads pt.shared_arrays + pt.fitsnap_dict['Testing']
     (svd.py:42-44); with arrays and trainall=True it fits all rows (svd.py:37-38)."""
     from types import SimpleNamespace
     from fitsnap_b200.solvers import SVD
     cfg = SimpleNamespace(sections={})
     s = SVD("SVD", _pt(ta["a"], ta["b"], ta["w"], ta["testing"]), cfg)
+    s.engine = engine
     s.perform_fit()
     assert isinstance(s.fit, np.ndarray) and s.fit.dtype == np.float64 and s.fit.shape == (31,)
     assert lf.coeff_rel_err(s.fit, ta["ref_svd_split"])[0] < 1e-10
     s2 = SVD("SVD", _pt(ta["a"], ta["b"], ta["w"]), cfg)
+    s2.engine = engine
     s2.perform_fit(a=ta["a"], b=ta["b"], w=ta["w"], trainall=True)
     assert lf.coeff_rel_err(s2.fit, ta["ref_svd"])[0] < 1e-10
     assert np.max(np.abs(s2.fit - ta["snapcoeff"])) < 1e-10
@@ -429,13 +431,14 @@ def test_solver_mirror_svd_shared_arrays_and_explicit(ta):
     assert s3.fit is None
 
 
-def test_solver_mirror_ridge_and_apply_transpose(ta):
+def test_solver_mirror_ridge_and_apply_transpose(engine, ta):
     from types import SimpleNamespace
     from fitsnap_b200.solvers import RIDGE
     a, b, w = ta["a"], ta["b"], ta["w"]
     cfg = SimpleNamespace(sections={"RIDGE": SimpleNamespace(alpha=1e-6, local_solver=0),
                                     "EXTRAS": SimpleNamespace(apply_transpose=0)})
     r = RIDGE("RIDGE", _pt(a, b, w), cfg)
+    r.engine = engine
     r.perform_fit(a=a, b=b, w=w, trainall=True)
     assert lf.coeff_rel_err(r.fit, lf.ridge_fit_exact(a, b, w, 1e-6))[0] < 1e-10
     assert lf.coeff_rel_err(r.fit, ta["ref_ridge_1e6"])[0] < 1e-6
@@ -450,6 +453,7 @@ def test_solver_mirror_ridge_and_apply_transpose(ta):
     cfg_t = SimpleNamespace(sections={"RIDGE": SimpleNamespace(alpha=alpha, local_solver=0),
                                       "EXTRAS": SimpleNamespace(apply_transpose=1)})
     rt = RIDGE("RIDGE", _pt(a, b, w, t), cfg_t)
+    rt.engine = engine
     rt.perform_fit()
     exact = lf.ridge_fit_exact(C, d, np.ones(len(d)), alpha)
     plain = lf.ridge_fit_exact(a, b, w, alpha, t)
@@ -457,7 +461,7 @@ def test_solver_mirror_ridge_and_apply_transpose(ta):
     assert lf.coeff_rel_err(rt.fit, plain)[1] > 1e-3          # and it is NOT ridge on A
 
 
-def test_hard_case_needs_adaptive_refinement():
+def test_hard_case_needs_adaptive_refinement(engine):
     """cond(w*A) ~ 2e7: fixed 2 rounds are not enough; the solver classes keep refining while the
     correction shrinks (one host sync per extra round)."""
     from types import SimpleNamespace
@@ -465,6 +469,7 @@ def test_hard_case_needs_adaptive_refinement():
     g = load_golden("solve_hard.npz")
     a, b, w, t = synth_system(**SOLVE_CASES["hard"])
     s = SVD("SVD", _pt(a, b, w, t), SimpleNamespace(sections={}))
+    s.engine = engine
     s.perform_fit()
     mr, l2, _ = lf.coeff_rel_err(s.fit, g["ref_svd"])
     assert l2 < 1e-7 and s.last_result.extra["refine_rounds"] > 2, (mr, l2, s.last_result.extra)
@@ -637,3 +642,65 @@ def test_streaming_fit_on_device_matches_reference(engine, ta, tmp_path):
     parts = [(a[i:j], b[i:j], w[i:j], t[i:j]) for i, j in zip(cuts[:-1], cuts[1:])]
     res = StreamingLinearFit(alpha=1e-6, refine=2, engine=engine).fit(parts)
     assert lf.coeff_rel_err(res.coefficients(), lf.ridge_fit_exact(a, b, w, 1e-6, t))[0] < 1e-10
+
+
+# ------------------------------------------------------------------------------- process_single (a3)
+SINGLE = [("snap_b0_efs", False), ("snap_b1_ef", False), ("snap_b0_es", False), ("snap_b1_fs", False),
+          ("pace_b0_efs", True), ("pace_b1_ef", True)]
+
+
+@pytest.mark.parametrize("tag,pace", SINGLE)
+def test_process_single_bit_exact_vs_reference_fixture(engine, tag, pace):
+    """`_collect_lammps_single` of the drop-in mixins (device scatter of one configuration) against the (a, b, w)
+    the unmodified reference's `process_single` returned for the same blocks (lammps_snap.py:224-389,
+    lammps_pace.py:197-366): bit-exact, incl. zero rows of switched-off families and default weights."""
+    from tests.stub_calc import fixture_configs, make_stub
+    g = load_golden("single_%s.npz" % tag)
+    calc = make_stub(engine, g, pace=pace)
+    ooff = np.concatenate([[0], np.cumsum(g["rows_per_config"])])
+    di = 0
+    for c, (d, block, vol, types) in enumerate(fixture_configs(g)):
+        a, b, w = calc.process_single(d, block, vol, types)
+        sl = slice(ooff[c], ooff[c + 1])
+        assert a.shape == g["ref_a"][sl].shape
+        assert np.array_equal(a, g["ref_a"][sl]) and np.array_equal(b, g["ref_b"][sl]) and np.array_equal(w, g["ref_w"][sl])
+        n = d["NumAtoms"]
+        nrows = int(g["use_energy"]) + 3 * n * int(g["use_force"]) + 6 * int(g["use_stress"])
+        di += nrows
+        assert calc.shared_index == nrows and calc.distributed_index == di
+
+
+def test_ridge_rank_deficient_falls_back_and_warns(engine):
+    """alpha > 0 with numerically dependent columns -- the Cholesky factor used to drop columns silently.
+    Now: a warning through pt.single_print and the eigenvalue-truncated ridge solve; result = sklearn's Ridge answer
+    for the same problem (which falls back to an SVD solve there)."""
+    from types import SimpleNamespace
+    from fitsnap_b200.solvers import RIDGE
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((4000, 20))
+    a[:, 7] = a[:, 2]                          # exactly dependent
+    a[:, 13] = a[:, 4] - a[:, 5]
+    b, w = rng.standard_normal(4000), np.ones(4000)
+    msgs = []
+    pt = _pt(a, b, w)
+    pt.single_print = lambda *m: msgs.append(" ".join(map(str, m)))
+    alpha = 1e-10
+    cfg = SimpleNamespace(sections={"RIDGE": SimpleNamespace(alpha=alpha, local_solver=0)})
+    r = RIDGE("RIDGE", pt, cfg)
+    r.engine = engine
+    r.perform_fit(a=a, b=b, w=w, trainall=True)
+    assert r.info["status"] == 1 and msgs and "rank deficient" in msgs[0]
+    ref = lf.ridge_fit_exact(a, b, w, alpha)
+    assert lf.coeff_rel_err(r.fit, ref)[1] < 1e-6
+
+
+def test_pageable_upload_through_the_pinned_ring(engine):
+    """Engine.to_device on ordinary (pageable) numpy arrays larger than one ring slot, odd sizes, int dtypes."""
+    rng = np.random.default_rng(1)
+    for shape in ((5_000_003,), (70_001, 131), (9, 7)):
+        a = rng.standard_normal(shape)
+        assert np.array_equal(engine.to_device(a).cpu().numpy(), a)
+    m = rng.integers(0, 2, 40_000_001).astype(np.uint8)
+    assert np.array_equal(engine.to_device(m, dtype=torch.uint8).cpu().numpy(), m)
+    a = rng.standard_normal((3000, 50))[:, ::2]             # non-contiguous view
+    assert np.array_equal(engine.to_device(a).cpu().numpy(), a)

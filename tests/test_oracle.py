@@ -117,3 +117,45 @@ def test_int8_gram_oracle_is_the_correctly_rounded_quantised_gram():
     aug2 = np.concatenate([a2 * w2[:, None], (w2 * b2)[:, None]], 1)
     assert np.array_equal(quantised_gram(a2, b2, w2), aug2.T @ aug2)
     assert slab_rows_for(1) == 128 and slab_rows_for(262144) == 262144 and slab_rows_for(600000) == 200064
+
+
+SINGLE = ["snap_b0_efs", "snap_b1_ef", "snap_b0_es", "snap_b1_fs", "pace_b0_efs", "pace_b1_ef"]
+
+
+@pytest.mark.parametrize("tag", SINGLE)
+def test_oracle_process_single_bit_exact(tag):
+    """`config_rows_single` == the unmodified reference's `process_single` output (fixtures written by
+    oracle/make_golden.py): zero rows for switched-off families, default weights of 1.0."""
+    g = load_golden("single_%s.npz" % tag)
+    nat = g["natoms"]
+    roff = np.concatenate([[0], np.cumsum(7 + 3 * nat.astype(np.int64))])
+    aoff = np.concatenate([[0], np.cumsum(nat.astype(np.int64))])
+    ooff = np.concatenate([[0], np.cumsum(g["rows_per_config"])])
+    drop = bool(g["weights_dropped"])
+    for c in range(len(nat)):
+        a, b, w = lf.config_rows_single(
+            g["raw"][roff[c]:roff[c + 1]], nat[c], g["volume"][c], g["energy"][c], g["forces"][3 * aoff[c]:3 * aoff[c + 1]],
+            g["stress"][c], None if drop else g["eweight"][c], None if drop else g["fweight"][c],
+            None if drop else g["vweight"][c], g["type_fraction"][c], int(g["numtypes"]), int(g["ncoeff"]),
+            int(g["bzeroflag"]), g["blank2j"], bool(g["use_energy"]), bool(g["use_force"]), bool(g["use_stress"]))
+        sl = slice(ooff[c], ooff[c + 1])
+        assert np.array_equal(a, g["ref_a"][sl]) and np.array_equal(b, g["ref_b"][sl]) and np.array_equal(w, g["ref_w"][sl])
+
+
+def test_reference_style_assembly_and_fit_equal_the_plain_restatement():
+    """The timing-faithful variants used by bench.py's reference arm (dense diag(blank2J) matmul, list masks, residual
+    product) compute the same numbers as the plain restatement."""
+    g = load_golden("scatter_snap_b0_efs.npz")
+    nat = g["natoms"]
+    roff = np.concatenate([[0], np.cumsum(7 + 3 * nat.astype(np.int64))])
+    aoff = np.concatenate([[0], np.cumsum(nat.astype(np.int64))])
+    cfgs = [dict(block=g["raw"][roff[c]:roff[c + 1]], natoms=int(nat[c]), volume=g["volume"][c], energy=g["energy"][c],
+                 forces=g["forces"][3 * aoff[c]:3 * aoff[c + 1]], stress=g["stress"][c], eweight=g["eweight"][c],
+                 fweight=g["fweight"][c], vweight=g["vweight"][c], type_fraction=g["type_fraction"][c])
+            for c in range(len(nat))]
+    a, b, w = lf.assemble_as_reference(cfgs, int(g["numtypes"]), int(g["ncoeff"]), int(g["bzeroflag"]), g["blank2j"])
+    assert np.array_equal(a, g["ref_a"]) and np.array_equal(b, g["ref_b"]) and np.array_equal(w, g["ref_w"])
+    t = g["ref_testing"]
+    x1, res = lf.ridge_perform_fit_as_reference(a, b, w, 1e-6, [bool(v) for v in t])
+    assert np.array_equal(x1, lf.ridge_fit(a, b, w, 1e-6, t)) and res.shape[0] == int((~t).sum())
+    assert np.array_equal(lf.svd_perform_fit_as_reference(a, b, w, [bool(v) for v in t]), lf.svd_fit(a, b, w, t))

@@ -188,3 +188,144 @@ def test_device_memory_guard_mirrors_the_reference_ram_guard(registered):
     cfg.sections["MEMORY"].override = True
     a, *_ = rd.ref_scatter(cfgs, blocks, vols, use_factory=True, context=(pt, cfg), **kw)
     assert a.shape[0] > 0
+
+
+@pytest.mark.parametrize("bz,efs,drop", [(0, (1, 1, 1), False), (1, (1, 1, 0), False), (0, (1, 0, 1), True),
+                                         (1, (0, 1, 1), False)])
+def test_process_single_after_register_equals_stock(registered, bz, efs, drop):
+    """lammps_base.py:101-125: `calculator.process_single(data, i) -> (a, b, w)` through the factory-made drop-in
+    equals the stock `_collect_lammps_single` (zero rows of switched-off families, default weights, indices)."""
+    rng = np.random.default_rng(5)
+    kw = dict(numtypes=2, types="In P", twojmax="6 4", bzeroflag=bz, energy=efs[0], force=efs[1], stress=efs[2])
+    pt0, cfg0 = rd.make_reference_context(**kw)
+    nc = cfg0.sections["BISPECTRUM"].ncoeff
+    cfgs, blocks, vols = _configs(rng, nc, 2, n_cfg=5)
+    ref, calc_ref = rd.ref_single(cfgs, blocks, vols, drop_weights=drop, **kw)
+    out, calc = rd.ref_single(cfgs, blocks, vols, use_factory=True, drop_weights=drop, **kw)
+    assert type(calc) is registered["LammpsSnap"]
+    for (a0, b0, w0), (a1, b1, w1) in zip(ref, out):
+        assert a0.shape == a1.shape and np.array_equal(a0, a1) and np.array_equal(b0, b1) and np.array_equal(w0, w1)
+    assert (calc.shared_index, calc.distributed_index) == (calc_ref.shared_index, calc_ref.distributed_index)
+
+
+def test_pace_process_single_after_register_equals_stock(registered):
+    rng = np.random.default_rng(6)
+    nc, nt = 11, 2
+    k = nc * nt + nt
+    ace = dict(numtypes=nt, ncoeff=nc, bzeroflag=0, bikflag=0, dgradflag=0, blank2J=np.ones(k),
+               type_mapping={"In": 1, "P": 2}, rcutfac=[4.0])
+    kw = dict(numtypes=nt, types="In P", twojmax="6 6", bzeroflag=0)
+    cfgs, blocks, vols = _configs(rng, nc, 2, n_cfg=4)
+    ref, _ = rd.ref_single(cfgs, blocks, vols, calculator="LAMMPSPACE", ace=ace, **kw)
+    out, calc = rd.ref_single(cfgs, blocks, vols, calculator="LAMMPSPACE", ace=ace, use_factory=True, **kw)
+    assert type(calc) is registered["LammpsPace"]
+    for r, o in zip(ref, out):
+        assert all(np.array_equal(x, y) for x, y in zip(r, o))
+
+
+def test_bikflag_layout_is_delegated_to_the_stock_collector(registered):
+    """with bikflag = 1 LAMMPS emits N energy rows per configuration; the drop-in must not reinterpret that
+    block -- it hands the configuration to the reference's own `_collect_lammps` (kept as `_ref_collect_lammps`)."""
+    rng = np.random.default_rng(12)
+    kw = dict(numtypes=1, types="Ta", twojmax="4", bzeroflag=1,
+              extra={"BISPECTRUM": {"bikflag": 1}, "CALCULATOR": {"per_atom_energy": 1}})
+    pt0, cfg0 = rd.make_reference_context(**kw)
+    nc = cfg0.sections["BISPECTRUM"].ncoeff
+    names = ["Ta"]
+    cfgs, blocks, vols = [], [], []
+    for i in range(4):
+        n = int(rng.integers(2, 6))
+        cfgs.append(rd.make_config_dict(n, 1, rng, names, group="g", fname="f%d" % i))
+        blocks.append(rng.standard_normal((n + 3 * n + 6, nc + 1)))      # bikflag: N energy rows
+        vols.append(100.0)
+    a_ref, b_ref, w_ref, lists_ref, *_ = rd.ref_scatter(cfgs, blocks, vols, **kw)
+    a, b, w, lists, _cfg, pt, calc = rd.ref_scatter(cfgs, blocks, vols, use_factory=True, **kw)
+    assert type(calc) is registered["LammpsSnap"] and calc._b200_stock_mode()
+    assert np.array_equal(a, a_ref) and np.array_equal(b, b_ref)
+    written = np.array(lists_ref["Row_Type"]) != "Energy"     # the reference leaves w of per-atom energy rows unset
+    assert np.array_equal(w[written], w_ref[written])
+    assert lists["Row_Type"] == lists_ref["Row_Type"]
+    assert not hasattr(pt, "fitsnap_b200_device")            # nothing was staged for the device
+
+
+def test_nonlinear_collectors_survive_register(registered):
+    """the network-solver path calls `_collect_lammps_preprocess` / `_collect_lammps_nonlinear`
+    (fitsnap.py:161-178); the drop-in classes keep the reference's own methods for them."""
+    from fitsnap3lib.calculators.lammps_snap import LammpsSnap as RefSnap
+    from fitsnap3lib.calculators.lammps_pace import LammpsPace as RefPace
+    for key, ref in (("LammpsSnap", RefSnap), ("LammpsPace", RefPace)):
+        cls = registered[key]
+        for meth in ("_collect_lammps_nonlinear", "_collect_lammps_preprocess", "_set_computes", "get_width"):
+            assert cls.__dict__[meth] is ref.__dict__[meth], (key, meth)
+        assert cls.__dict__["_ref_collect_lammps"] is ref.__dict__["_collect_lammps"]
+
+
+def test_host_mirror_is_lazy_and_in_place_edits_win(registered):
+    """The rows assembled on the device reach pt.shared_arrays only when `.array` is read; once it has been read the
+    solver must not trust the device copy of that array any more (in-place edits were silently ignored)."""
+    from fitsnap3lib.solvers.solver_factory import solver
+    from fitsnap_b200.hostmirror import LazyHostMirror
+    rng = np.random.default_rng(8)
+    kw = dict(numtypes=1, types="Ta", twojmax="4", bzeroflag=0)
+    pt0, cfg0 = rd.make_reference_context(**kw)
+    nc = cfg0.sections["BISPECTRUM"].ncoeff
+    cfgs, blocks, vols = _configs(rng, nc, 1, n_cfg=40)
+    a_ref, b_ref, w_ref, lists_ref, *_ = rd.ref_scatter(cfgs, blocks, vols, **kw)
+    # drive the drop-in by hand so that nothing reads `.array` behind our back
+    from fitsnap3lib.calculators.calculator_factory import calculator as make_calculator
+    pt, cfg = rd.make_reference_context(**kw)
+    calc = make_calculator("LAMMPSSNAP", pt, cfg)
+    calc._prepare_lammps = lambda: calc._set_structure()
+    calc.shared_index = calc.distributed_index = 0
+    calc.allocate_per_config(cfgs)
+    calc.create_a()
+    for i, c in enumerate(cfgs):
+        rd.FakeLammps.staged_block, rd.FakeLammps.staged_volume = blocks[i], vols[i]
+        calc.process_configs(c, i)
+    calc.collect_distributed_lists()
+    ma, mw = pt.shared_arrays["a"], pt.shared_arrays["w"]
+    assert isinstance(ma, LazyHostMirror) and ma.pending and not ma.exposed
+    s = solver("SVD", pt, cfg)
+    s.refine = 2
+    s.perform_fit()
+    assert ma.pending and not ma.exposed                      # the fit read the device rows, A never came back
+    x0 = s.fit.copy()
+    mw.array[:] *= np.where(np.array(lists_ref["Row_Type"]) == "Energy", 7.0, 1.0)   # in-place edit of the weights
+    assert mw.exposed and ma.pending
+    s.perform_fit()
+    x_ref, _ = rd.ref_fit("SVD", a_ref, b_ref, pt.shared_arrays["w"].array, testing=np.array(lists_ref["Testing"]))
+    assert np.max(np.abs(s.fit - x_ref)) < 1e-9 * np.max(np.abs(x_ref))
+    assert np.max(np.abs(s.fit - x0)) > 1e-6 * np.max(np.abs(x0))
+    assert np.array_equal(pt.shared_arrays["a"].array, a_ref) and not ma.pending      # reading A materialises it
+
+
+def test_error_analysis_override_equals_the_stock_table_and_offsets(registered):
+    """`FitSnap.perform_fit` calls `solver.error_analysis()` (fitsnap.py:213-220): the drop-in's override fills
+    `solver.errors` like solver.py:368-429 does (device sums instead of DataFrame(a)) and applies `_offset`."""
+    from fitsnap3lib.solvers.solver_factory import solver
+    from fitsnap3lib.solvers.solver import Solver
+    rng = np.random.default_rng(31)
+    kw = dict(numtypes=2, types="In P", twojmax="4 4", bzeroflag=1)
+    pt0, cfg0 = rd.make_reference_context(**kw)
+    nc = cfg0.sections["BISPECTRUM"].ncoeff
+    cfgs, blocks, vols = _configs(rng, nc, 2, n_cfg=50)
+    a, b, w, lists, cfg, pt, calc = rd.ref_scatter(cfgs, blocks, vols, use_factory=True, **kw)
+    s = solver("SVD", pt, cfg)
+    s.refine = 2
+    s.perform_fit()
+    raw = s.fit.copy()
+    s.error_analysis()
+    dev_err, dev_fit = s.errors.copy(), np.asarray(s.fit).copy()
+    assert dev_fit.shape == (2 * (nc + 1), 1) and dev_fit[0, 0] == 0.0        # _offset applied (bzeroflag = 1)
+    df = s.df
+    assert {"truths", "preds", "weights", "Groups", "Row_Type", "Testing"} <= set(df.columns) and len(df) == a.shape[0]
+    s.fit = raw
+    Solver.error_analysis(s)                                                  # the reference's implementation
+    ref_err = s.errors
+    assert list(dev_err.index) == list(ref_err.index) and list(dev_err.columns) == list(ref_err.columns)
+    assert np.array_equal(dev_err["ncount"].values, ref_err["ncount"].values)
+    for col in ("mae", "rmse", "rsq"):
+        r, d = ref_err[col].values.astype(float), dev_err[col].values.astype(float)
+        ok = np.isclose(d, r, rtol=1e-9, atol=1e-12) | (np.isnan(d) & np.isnan(r)) | (~np.isfinite(r) & ~np.isfinite(d))
+        assert ok.all(), col
+    assert np.array_equal(np.asarray(s.fit), dev_fit)
