@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint8, c_uint64, c_void_p
 
 LIB_NAME = "libfitsnap_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", LIB_NAME)
@@ -27,6 +27,18 @@ SIGNATURES = {
     "fsb_create": (c_int, [POINTER(c_void_p), c_int]),
     "fsb_destroy": (c_int, [c_void_p]),
     "fsb_sm_count": (c_int, [c_void_p, POINTER(c_int)]),
+    "fsb_launch_count": (c_int, [c_void_p, POINTER(c_uint64)]),
+    "fsb_comm_unique_id": (c_int, [c_void_p, c_size_t]),
+    "fsb_comm_init": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "fsb_comm_adopt": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "fsb_comm_peer_handle_bytes": (c_size_t, []),
+    "fsb_comm_peer_max_bytes": (c_size_t, []),
+    "fsb_comm_peer_export": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "fsb_comm_peer_attach": (c_int, [c_void_p, c_void_p, c_int]),
+    "fsb_comm_peer_disable": (c_int, [c_void_p]),
+    "fsb_comm_info": (c_int, [c_void_p, POINTER(c_int64)]),
+    "fsb_allreduce": (c_int, [c_void_p, c_void_p, _P, c_int64, c_void_p]),
+    "fsb_comm_destroy": (c_int, [c_void_p]),
     "fsb_scatter": (c_int, [c_void_p, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                             c_int32, c_int32, c_int32, c_int32, _P, c_int64, _P, _P, c_int64, _P, _P, c_void_p]),
     "fsb_set_gram_path": (c_int, [c_void_p, c_int32]),
@@ -95,5 +107,5 @@ def check(fn_name, status):
     if status != 0:
         lib = load()
         text = lib.fsb_status_string(status).decode()
-        cuda_text = lib.fsb_last_cuda_error().decode() if status == 2 else ""
+        cuda_text = lib.fsb_last_cuda_error().decode() if status in (2, 4) else ""
         raise FsbError(fn_name, status, text, cuda_text)

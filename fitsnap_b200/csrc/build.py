@@ -21,7 +21,7 @@ LIB_DIR = os.path.join(PKG, "_lib")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB_PATH = os.path.join(LIB_DIR, "libfitsnap_b200.so")
 
-SOURCES = ["fsb_api.cu", "gram.cu", "solve.cu", "stream_ops.cu", "lasso.cu", "gram_small.cu", "gram_tma.cu", "pinv.cu", "gram_i8.cu"]
+SOURCES = ["fsb_api.cu", "gram.cu", "solve.cu", "stream_ops.cu", "lasso.cu", "gram_small.cu", "gram_tma.cu", "pinv.cu", "gram_i8.cu", "comm.cu"]
 HEADERS = ["fsb_common.cuh", os.path.join(ROOT, "include", "fitsnap_b200.h")]
 
 NVCC_FLAGS = [
@@ -74,7 +74,7 @@ def build(force=False, verbose=False):
     if verbose:
         print(log)
     cmd = [nvcc, "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-o", LIB_PATH] + objs
+           "-o", LIB_PATH] + objs + ["-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -49,6 +49,12 @@ void fsb_note_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 
+void fsb_note_text(const char* where, const char* detail) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, detail ? detail : "");
+}
+
+unsigned long long g_fsb_launches = 0;
+
 static const int FSB_MAX_K = 2047;  // rowpass kernels hold ceil(k/32) <= 64 values per lane
 
 extern "C" {
@@ -103,6 +109,12 @@ int fsb_create(fsb_handle_t* out, int device) {
 
 int fsb_destroy(fsb_handle_t h) {
   delete h;
+  return FSB_OK;
+}
+
+int fsb_launch_count(fsb_handle_t h, uint64_t* count) {
+  if (!h || !count) return FSB_ERR_INVALID_ARGUMENT;
+  *count = (uint64_t)g_fsb_launches;
   return FSB_OK;
 }
 

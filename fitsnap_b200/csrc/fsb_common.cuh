@@ -14,6 +14,9 @@ struct fsb_context {
 
 // thread-local last CUDA error text (fsb_last_cuda_error)
 void fsb_note_cuda_error(cudaError_t e, const char* where);
+void fsb_note_text(const char* where, const char* detail);
+// kernels launched by this library in this process (fsb_launch_count): bumped once per successful launch
+extern unsigned long long g_fsb_launches;
 
 #define FSB_CUDA_TRY(expr)                                   \
   do {                                                       \
@@ -31,6 +34,7 @@ void fsb_note_cuda_error(cudaError_t e, const char* where);
       fsb_note_cuda_error(_e, where);                        \
       return FSB_ERR_CUDA;                                   \
     }                                                        \
+    ++g_fsb_launches;                                        \
   } while (0)
 
 static inline int64_t fsb_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

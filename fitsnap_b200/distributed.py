@@ -70,3 +70,38 @@ def attach(target, group=None, engine=None):
     if calc is not None:
         calc._b200_engine = eng
     return solver
+
+
+def bind_to_gpu_numa(local_gpu):
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off (sysfs `numa_node` of the GPU's PCI
+    function), so that the pinned staging buffers it allocates afterwards are first-touched on that node and its H2D
+    copies do not cross the socket interconnect.  With 8 ranks staging at once from one node the per-GPU H2D rate
+    halved in round 1 (55.6 -> 27.4 GB/s).  Returns a short description, or None when the topology cannot be read
+    (single-node boxes, containers without sysfs) -- never raises."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(local_gpu))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:            # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return None
+        os.sched_setaffinity(0, use)
+        return "gpu %d (%s) -> numa node %d, %d cpus" % (int(local_gpu), bus, node, len(use))
+    except Exception:
+        return None

@@ -129,9 +129,30 @@ class Engine:
         self.sm_count = n.value
         self._ws = {}
         self._stager = None
-        self.launch_count = 0
+        self._comms = {}
+
+    @property
+    def launch_count(self):
+        """Kernels this library has launched so far (counted inside the library at every launch site)."""
+        n = ctypes.c_uint64()
+        _cabi.check("fsb_launch_count", self.lib.fsb_launch_count(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    def comm_for(self, group):
+        """The device communicator (`DeviceComm`: NCCL + NVLink peer windows behind `fsb_allreduce`) bound to a
+        torch.distributed group; created collectively on first use."""
+        c = self._comms.get(group)
+        if c is None:
+            c = self._comms[group] = DeviceComm(self, group)
+        return c
 
     def __del__(self):
+        try:
+            for c in getattr(self, "_comms", {}).values():
+                c.close()
+            self._comms = {}
+        except Exception:
+            pass
         try:
             if getattr(self, "_h", None):
                 self.lib.fsb_destroy(self._h)
@@ -206,13 +227,6 @@ class Engine:
         ws = self._workspace("gram", nbytes)
         _cabi.check("fsb_gram", self.lib.fsb_gram(self._h, _ptr(A), lda, _ptr(b), _ptr(w), _ptr(testing), n, k,
                                                    _ptr(gaug), _ptr(ws), ws.numel(), self._stream()))
-        if self.gram_path(n, k) == "int8":
-            # per slab of 2^18 rows: column maxima, residue conversion, tcgen05 GEMM, CRT
-            self.launch_count += 4 * max(1, -(-n // 262144))
-        else:
-            # narrow: row-split kernel + reduce; wide: pre-weight + TMA kernel + reduce
-            self.launch_count += 2 if k + 1 <= 128 else 3
-        self.launch_count += 1 if (testing is not None and n > 0) else 0
         return gaug
 
     def factor(self, gaug, alpha=0.0):
@@ -223,14 +237,6 @@ class Engine:
         info = torch.empty(_cabi.INFO_LEN, dtype=torch.int32, device=self.device)
         _cabi.check("fsb_factor", self.lib.fsb_factor(self._h, _ptr(gaug), k, float(alpha), _ptr(buf), nbytes,
                                                        _ptr(info), self._stream()))
-        npanel = (k + 63) // 64
-        if k <= 128:
-            self.launch_count += 1
-        else:
-            # init + equilibrate + blocked Cholesky (potrf / trsm / syrk per panel) + explicit inverse of L
-            # (diagonal blocks, then two tile-GEMM launches per doubling level)
-            levels = max(0, (npanel - 1).bit_length())
-            self.launch_count += 2 + npanel + 2 * max(npanel - 1, 0) + 1 + 2 * levels
         return Factor(buf, info, k, float(alpha))
 
     def solve(self, factor, rhs, rhs_stride=1, x_in=None, out=None):
@@ -239,7 +245,6 @@ class Engine:
         _cabi.check("fsb_factor_solve",
                     self.lib.fsb_factor_solve(self._h, _ptr(factor.buf), k, _ptr(rhs), int(rhs_stride),
                                               factor.alpha, _ptr(x_in), _ptr(x), self._stream()))
-        self.launch_count += 1 if k <= 128 else 2      # k > 128: forward + backward GEMV with the explicit inverse
         return x
 
     def pinv_factor(self, gaug, rcond=None):
@@ -252,14 +257,12 @@ class Engine:
         info = torch.zeros(2, dtype=torch.int32, device=self.device)
         _cabi.check("fsb_pinv_factor", self.lib.fsb_pinv_factor(self._h, _ptr(gaug), k, float(rcond), _ptr(buf), nbytes,
                                                                  _ptr(info), self._stream()))
-        self.launch_count += 2
         return PinvFactor(buf, info, k)
 
     def pinv_apply(self, pf, rhs, rhs_stride=1, x_in=None):
         x = torch.empty(pf.k, dtype=torch.float64, device=self.device)
         _cabi.check("fsb_pinv_apply", self.lib.fsb_pinv_apply(self._h, _ptr(pf.buf), pf.k, _ptr(rhs), int(rhs_stride),
                                                                _ptr(x_in), _ptr(x), self._stream()))
-        self.launch_count += 1
         return x
 
     def lasso(self, gaug, n_train, alpha, max_iter=2000, tol=1e-12):
@@ -269,7 +272,6 @@ class Engine:
         info = torch.empty(2, dtype=torch.int32, device=self.device)
         _cabi.check("fsb_lasso", self.lib.fsb_lasso(self._h, _ptr(gaug), k, int(n_train), float(alpha), int(max_iter),
                                                      float(tol), _ptr(x), _ptr(info), self._stream()))
-        self.launch_count += 1
         return x, info
 
     def residual(self, A, b, w, testing, x):
@@ -281,7 +283,6 @@ class Engine:
         _cabi.check("fsb_residual", self.lib.fsb_residual(self._h, _ptr(A), lda, _ptr(b), _ptr(w), _ptr(testing),
                                                            n, k, _ptr(x), _ptr(g), _ptr(ws), ws.numel(),
                                                            self._stream()))
-        self.launch_count += 2
         return g
 
     def predict(self, A, x):
@@ -290,7 +291,6 @@ class Engine:
         lda = A.stride(0) if n > 1 else max(k, A.stride(0))
         y = torch.empty(n, dtype=torch.float64, device=self.device)
         _cabi.check("fsb_predict", self.lib.fsb_predict(self._h, _ptr(A), lda, n, k, _ptr(x), _ptr(y), self._stream()))
-        self.launch_count += 1 if n > 0 else 0
         return y
 
     def group_stats(self, A, b, w, group_id, x, n_groups):
@@ -301,7 +301,6 @@ class Engine:
         _cabi.check("fsb_group_stats", self.lib.fsb_group_stats(self._h, _ptr(A), lda, _ptr(b), _ptr(w), _ptr(group_id),
                                                                  n, k, _ptr(x), int(n_groups), _ptr(stats),
                                                                  self._stream()))
-        self.launch_count += 1 if n > 0 else 0
         return stats
 
     def scatter(self, batch, A=None, b=None, w=None, lda=None):
@@ -320,7 +319,6 @@ class Engine:
             _ptr(batch.eweight), _ptr(batch.fweight), _ptr(batch.vweight), _ptr(batch.type_fraction),
             _ptr(batch.blank2j), batch.ncfg, batch.numtypes, batch.ncoeff, batch.flags,
             _ptr(A), A.stride(0) if A.shape[0] > 1 else lda, _ptr(b), _ptr(w), n_out, _ptr(batch.row_cfg), _ptr(nonfinite), self._stream()))
-        self.launch_count += 1 if (n_out > 0 and batch.ncfg > 0) else 0
         return A, b, w, nonfinite
 
     # ------------------------------------------------------------------ the fit
@@ -331,9 +329,78 @@ class Engine:
         return refine_rows(self, A, b, w, testing, res, group=group)
 
 
-def _all_reduce(t, group):
+class DeviceComm:
+    """`fsb_comm_t` bound to the ranks of a torch.distributed group: torch.distributed is only the OUT-OF-BAND channel
+    that ships the NCCL unique id and the CUDA IPC handles of the peer windows at set-up; every all-reduce of the fit
+    afterwards is one `fsb_allreduce` on the caller's stream (NVLink peer-window kernel for the small Gram / k-vector
+    messages, ncclAllReduce for large ones) -- see csrc/comm.cu.  `FSB_NO_PEER=1` keeps everything on NCCL."""
+
+    def __init__(self, engine, group):
+        import socket
+        import torch.distributed as dist
+        self.engine, self.group = engine, group
+        lib = engine.lib
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self._c = None
+        idbuf = ctypes.create_string_buffer(128)
+        if self.rank == 0:
+            _cabi.check("fsb_comm_unique_id", lib.fsb_comm_unique_id(idbuf, 128))
+        box = [bytes(idbuf.raw) if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0), group=group)
+        c = ctypes.c_void_p()
+        _cabi.check("fsb_comm_init", lib.fsb_comm_init(engine._h, box[0], self.world, self.rank, ctypes.byref(c)))
+        self._c = c
+        # peer windows: ranks of one box only, and only if every rank could map every window
+        self.peer = False
+        if self.world > 1 and not os.environ.get("FSB_NO_PEER"):
+            hb = int(lib.fsb_comm_peer_handle_bytes())
+            hbuf = ctypes.create_string_buffer(hb)
+            st = lib.fsb_comm_peer_export(self._c, hbuf, hb)
+            mine = (socket.gethostname(), bytes(hbuf.raw) if st == 0 else None)
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine, group=group)
+            ok = all(h is not None and host == everyone[0][0] for host, h in everyone)
+            if ok:
+                ok = lib.fsb_comm_peer_attach(self._c, b"".join(h for _host, h in everyone), self.world) == 0
+            votes = [None] * self.world
+            dist.all_gather_object(votes, bool(ok), group=group)
+            self.peer = all(votes)
+            if not self.peer:
+                lib.fsb_comm_peer_disable(self._c)
+        self.peer_max_bytes = int(lib.fsb_comm_peer_max_bytes())
+
+    def all_reduce(self, t):
+        assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        _cabi.check("fsb_allreduce", self.engine.lib.fsb_allreduce(self.engine._h, self._c, _ptr(t), t.numel(),
+                                                                   self.engine._stream()))
+        return t
+
+    def uses_peer(self, numel):
+        return self.peer and numel * 8 <= self.peer_max_bytes
+
+    def info(self):
+        out = (ctypes.c_int64 * 4)()
+        _cabi.check("fsb_comm_info", self.engine.lib.fsb_comm_info(self._c, out))
+        return {"peer_windows": bool(out[0]), "peer_calls": int(out[1]), "nccl_calls": int(out[2]), "world": int(out[3])}
+
+    def close(self):
+        if self._c is not None:
+            self.engine.lib.fsb_comm_destroy(self._c)
+            self._c = None
+
+
+def _all_reduce(t, group, engine=None):
+    """In-place sum of `t` over `group`.  Device tensors of a real Engine go through the library's own collective
+    (`fsb_allreduce`); host tensors (the gloo tests of the host logic) through torch.distributed."""
     import torch.distributed as dist
-    if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if group is None or not dist.is_initialized() or dist.get_world_size(group) <= 1:
+        return
+    if t.is_cuda and hasattr(engine, "comm_for") and t.dtype == torch.float64:
+        if not t.is_contiguous():
+            raise ValueError("all-reduce of a non-contiguous device tensor")
+        engine.comm_for(group).all_reduce(t)
+    else:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
@@ -351,14 +418,14 @@ def fit_rows(engine, A, b, w, testing=None, alpha=0.0, refine=2, group=None, dia
     start = getattr(engine, "launch_count", 0)
     if gaug is None:                 # a caller that streamed the rows in has accumulated it already
         gaug = engine.gram(A, b, w, testing)
-    _all_reduce(gaug, group)
+    _all_reduce(gaug, group, engine)
     k = gaug.shape[0] - 1
     f = engine.factor(gaug, alpha)
     x = engine.solve(f, gaug[:, k], rhs_stride=k + 1)
     last = None
     for _ in range(int(refine)):
         g = engine.residual(A, b, w, testing, x)
-        _all_reduce(g, group)
+        _all_reduce(g, group, engine)
         x_new = engine.solve(f, g, x_in=x)
         if diagnostics:
             last = (x_new - x).abs().max() / x_new.abs().max().clamp_min(1e-300)
@@ -384,7 +451,7 @@ def fit_rows_min_norm(engine, A, b, w, testing, gaug, refine=3, group=None, rcon
     last = None
     for _ in range(int(refine)):
         g = engine.residual(A, b, w, testing, x)
-        _all_reduce(g, group)
+        _all_reduce(g, group, engine)
         if alpha:
             g = g - float(alpha) * x
         x_new = engine.pinv_apply(pf, g, x_in=x)
@@ -399,7 +466,7 @@ def refine_rows(engine, A, b, w, testing, res, group=None):
     start = getattr(engine, "launch_count", 0)
     f = res.extra["factor"]
     g = engine.residual(A, b, w, testing, res.x)
-    _all_reduce(g, group)
+    _all_reduce(g, group, engine)
     x_new = engine.solve(f, g, x_in=res.x)
     last = (x_new - res.x).abs().max() / x_new.abs().max().clamp_min(1e-300)
     return FitResult(x=x_new, gaug=res.gaug, info=res.info, last_correction=last,

@@ -105,8 +105,8 @@ def linear_error_analysis(engine, A, b, w, fs_dict, x, group=None):
         keys = all_keys
     stats = engine.group_stats(A, b, w, engine.to_device(gid, dtype=torch.int32), x, len(keys))
     if sharded:
-        import torch.distributed as dist
-        dist.all_reduce(stats, group=group)
+        from .engine import _all_reduce
+        _all_reduce(stats, group, engine)
     return errors_frame(stats.cpu().numpy(), keys)
 
 

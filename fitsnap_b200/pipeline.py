@@ -199,7 +199,7 @@ class StreamingLinearFit:
             n_rows += int(A.shape[0])
         if gaug is None:
             raise ValueError("StreamingLinearFit.fit: no chunks")
-        _all_reduce(gaug, self.group)
+        _all_reduce(gaug, self.group, eng)
         k = gaug.shape[0] - 1
         f = eng.factor(gaug, self.alpha)
         x = eng.solve(f, gaug[:, k], rhs_stride=k + 1)
@@ -209,7 +209,7 @@ class StreamingLinearFit:
                 A, B, W, T = self._device_chunk(chunk)
                 g = eng.residual(A, B, W, T, x)
                 gsum = g if gsum is None else gsum.add_(g)
-            _all_reduce(gsum, self.group)
+            _all_reduce(gsum, self.group, eng)
             x = eng.solve(f, gsum, x_in=x)
         return FitResult(x=x, gaug=gaug, info=f.info, launches=getattr(eng, "launch_count", 0) - start,
                          extra={"factor": f, "rows_streamed": n_rows})
@@ -246,11 +246,21 @@ class CapturedStep:
     group weights: rewrite `batch.eweight/fweight/vweight` in place, replay).  The buffers of `batch`, `testing`
     and `out` are baked into the graph by address; results land in the same `FitResult` tensors on every replay.
     All launches go through the C-ABI on the capturing stream; the library allocates nothing and never
-    synchronises, so the path is capturable as is."""
+    synchronises, so the path is capturable as is -- including the row-sharded step, whose all-reduces are the
+    library's own peer-window kernel (`fsb_allreduce`, csrc/comm.cu): an ordinary kernel node, no communicator
+    stream (every rank must capture and replay the same sequence)."""
 
     def __init__(self, pipe: LinearFitPipeline, batch: ConfigBatch, testing=None, out=None, warmup=2):
         self.pipe, self.batch = pipe, batch
         dev = pipe.engine.device
+        if pipe.group is not None:
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size(pipe.group) > 1:
+                comm = pipe.engine.comm_for(pipe.group)
+                if not comm.uses_peer((batch.k + 1) ** 2):
+                    raise RuntimeError("CapturedStep: the Gram all-reduce of this shape goes through NCCL; only the "
+                                       "peer-window collective (fsb_allreduce <= %d bytes) is captured into a graph"
+                                       % comm.peer_max_bytes)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):            # warm-up: workspaces, function attributes, NCCL channels

@@ -308,9 +308,7 @@ class RIDGE(LinearSolverBase):
             A, B, W, T = self._to_device(a, b, w, testing)
             eng = self._engine()
             gaug = eng.gram(A, B, W, T)
-            if self.process_group is not None:
-                import torch.distributed as dist
-                dist.all_reduce(gaug, group=self.process_group)
+            _engine._all_reduce(gaug, self.process_group, eng)
             k = gaug.shape[0] - 1
             C = gaug[:k, :k].contiguous()
             d = gaug[:k, k].contiguous()
@@ -348,10 +346,9 @@ class LASSO(LinearSolverBase):
         gaug = eng.gram(A, B, W, T)
         n_train = A.shape[0] if T is None else int(A.shape[0] - int(T.sum().item()))
         if self.process_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(gaug, group=self.process_group)
+            _engine._all_reduce(gaug, self.process_group, eng)
             nt = torch.tensor([n_train], dtype=torch.float64, device=gaug.device)
-            dist.all_reduce(nt, group=self.process_group)
+            _engine._all_reduce(nt, self.process_group, eng)
             n_train = int(nt.item())
         extras = _section(self.config, "EXTRAS")
         if _get(extras, "apply_transpose", False):
@@ -400,8 +397,7 @@ class ANL(LinearSolverBase):
         eng = self._engine()
         gaug = eng.gram(A, B, W, T)
         if sharded:
-            import torch.distributed as dist
-            dist.all_reduce(gaug, group=self.process_group)
+            _engine._all_reduce(gaug, self.process_group, eng)
         k = A.shape[1]
         gh = gaug.cpu().numpy()
         nugget = self._alpha()
@@ -412,7 +408,7 @@ class ANL(LinearSolverBase):
         gid = torch.zeros(A.shape[0], dtype=torch.int32, device=eng.device) if T is None else T.to(torch.int32)
         stats = eng.group_stats(A, B, W, gid, eng.to_device(self.fit), 2)
         if sharded:
-            dist.all_reduce(stats, group=self.process_group)
+            _engine._all_reduce(stats, self.process_group, eng)
         stats = stats.cpu().numpy()
         npt, wsq = float(stats[0, 0]), float(stats[0, 7])
         sigmahat = (wsq / 2.0) / ((npt - k) / 2.0 - 1.0)                         # anl.py:48-52

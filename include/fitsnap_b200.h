@@ -68,6 +68,9 @@ const char* fsb_last_cuda_error(void);
 int fsb_create(fsb_handle_t* out, int device);
 int fsb_destroy(fsb_handle_t h);
 int fsb_sm_count(fsb_handle_t h, int* sm_count);
+/* kernels this library has launched in the calling process so far (a real counter, bumped at every launch site);
+ * bench.py's `gpu_launches` is a difference of two readings. */
+int fsb_launch_count(fsb_handle_t h, uint64_t* count);
 
 /* ---- K1: row build + scale + scatter ------------------------------------------------
  * Replaces LammpsSnap._collect_lammps (calculators/lammps_snap.py:391-556) and
@@ -130,6 +133,40 @@ size_t fsb_gram_workspace_bytes(fsb_handle_t h, int64_t n_rows, int32_t k);
 int fsb_gram(fsb_handle_t h, const double* A, int64_t lda, const double* b, const double* w,
              const uint8_t* testing, int64_t n_rows, int32_t k, double* gaug,
              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K5: the collective of the row-sharded fit -------------------------------------------
+ * Replaces comm.Allreduce([c, MPI.DOUBLE], [c_all, MPI.DOUBLE]) / ([d, ...]) of
+ * examples/library/transpose_trick/example.py:241-242 (and the node-shared-array reductions of
+ * parallel_tools.py): in-place SUM of `count` doubles over the ranks of a communicator, on the caller's stream.
+ * One process per GPU; every rank makes the same sequence of calls with the same counts.
+ *
+ * Communicator set-up (host side, once):
+ *   rank 0: fsb_comm_unique_id(id)  ->  ship the 128 bytes to every rank (MPI_Bcast, a torch.distributed store ...)
+ *   all   : fsb_comm_init(h, id, world, rank, &comm)            -- ncclCommInitRank (libnccl.so.2 is dlopen'ed)
+ *      or : fsb_comm_adopt(h, existing_ncclComm_t, world, rank, &comm)
+ *   optional peer windows for small messages (ranks of ONE box, NVLink / NVSwitch):
+ *   all   : fsb_comm_peer_export(comm, handle)  ->  all-gather the handles (fsb_comm_peer_handle_bytes() each)
+ *   all   : fsb_comm_peer_attach(comm, handles_in_rank_order, world)   -- cudaIpcOpenMemHandle
+ *           (if it fails on ANY rank, every rank must call fsb_comm_peer_disable)
+ * fsb_allreduce then sends messages of at most fsb_comm_peer_max_bytes() through ONE kernel that stages the vector
+ * in this rank's window, publishes an epoch flag, waits for every rank's flag and adds all windows in rank order over
+ * peer loads (bit-identical sums on every rank; CUDA-graph capturable; no communicator stream), and larger messages
+ * through ncclAllReduce(ncclDouble, ncclSum).  Ranks must enter a peer-window call within FSB_PEER_TIMEOUT_S
+ * (default 120 s) of each other, otherwise the waiting kernel traps instead of hanging the device.
+ * fsb_comm_info: out4 = {peer windows ready, peer-window calls, NCCL calls, world}.
+ */
+typedef struct fsb_comm* fsb_comm_t;
+int fsb_comm_unique_id(void* id, size_t id_bytes);   /* id_bytes >= 128 */
+int fsb_comm_init(fsb_handle_t h, const void* id, int world, int rank, fsb_comm_t* out);
+int fsb_comm_adopt(fsb_handle_t h, void* nccl_comm, int world, int rank, fsb_comm_t* out);
+size_t fsb_comm_peer_handle_bytes(void);
+size_t fsb_comm_peer_max_bytes(void);
+int fsb_comm_peer_export(fsb_comm_t c, void* handle, size_t handle_bytes);
+int fsb_comm_peer_attach(fsb_comm_t c, const void* handles, int n);
+int fsb_comm_peer_disable(fsb_comm_t c);
+int fsb_comm_info(fsb_comm_t c, int64_t* out4);
+int fsb_allreduce(fsb_handle_t h, fsb_comm_t c, double* buf, int64_t count, void* stream);
+int fsb_comm_destroy(fsb_comm_t c);
 
 /* ---- K6: factor + solve -------------------------------------------------------------
  * Replaces scipy.linalg.lstsq(aw,bw,1e-13) as called at solvers/svd.py:54 (alpha = 0) and

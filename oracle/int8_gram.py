@@ -63,3 +63,61 @@ def quantised_gram(a, b, w, testing=None):
         g = _slab_gram(aug[r0:r0 + step])
         total = g if total is None else total + g
     return total
+
+
+# --------------------------------------------------------------------------------------------------
+# The same definition, fast enough for BASELINE-sized matrices: the 53-bit integers q are cut into four
+# 14-bit limbs; a limb-by-limb product summed over at most 2^18 rows stays below 2^46, so every one of the
+# 16 limb Grams is EXACT in an fp64 dgemm.  Only the final recombination  G' = sum 2^(14(p+q)) P_pq  runs in
+# Python integers (k^2 of them).  tests/test_oracle.py pins this function to `quantised_gram` bit for bit.
+_LIMB_BITS = 14
+_NLIMB = 4
+
+
+def _slab_gram_fast(aug):
+    k1 = aug.shape[1]
+    n = aug.shape[0]
+    assert n <= (1 << 18)
+    m = np.abs(aug).max(axis=0) if n else np.zeros(k1)
+    e = np.zeros(k1, dtype=np.int64)
+    nz = m > 0.0
+    e[nz] = np.clip(BETA - 1 - (np.frexp(m[nz])[1] - 1), -1000, 1000)
+    q = np.rint(aug * np.ldexp(1.0, e)[None, :])                  # integer-valued, |q| < 2^53 (one value may be 2^53)
+    sign = np.sign(q)
+    mag = np.abs(q)
+    limbs = []
+    base = float(1 << _LIMB_BITS)
+    for _ in range(_NLIMB):                                       # exact: mag is an integer below 2^54
+        hi = np.floor(mag / base)
+        limbs.append(sign * (mag - hi * base))
+        mag = hi
+    assert not mag.any()
+    gint = np.zeros((k1, k1), dtype=object)
+    for p in range(_NLIMB):
+        for r in range(p, _NLIMB):
+            blk = limbs[p].T @ limbs[r]                           # exact in fp64 (< 2^46)
+            if r != p:
+                blk = blk + blk.T
+            gint += np.vectorize(int, otypes=[object])(blk) * (1 << (_LIMB_BITS * (p + r)))
+    out = np.empty((k1, k1))
+    for i in range(k1):
+        ei = int(e[i])
+        for j in range(k1):
+            out[i, j] = math.ldexp(float(int(gint[i, j])), -(ei + int(e[j])))
+    return out
+
+
+def quantised_gram_fast(a, b, w, testing=None):
+    """`quantised_gram`, through exact fp64 limb products (BLAS) instead of Python integers."""
+    a = np.asarray(a, dtype=np.float64)
+    n, k = a.shape
+    wv = np.asarray(w, dtype=np.float64).copy()
+    if testing is not None:
+        wv[np.asarray(testing, dtype=bool)] = 0.0
+    aug = np.concatenate([wv[:, None] * a, (wv * np.asarray(b, dtype=np.float64))[:, None]], axis=1)
+    step = slab_rows_for(n)
+    total = None
+    for r0 in range(0, max(n, 1), step):
+        g = _slab_gram_fast(aug[r0:r0 + step])
+        total = g if total is None else total + g
+    return total

@@ -223,11 +223,36 @@ def save_single(tag, cfgs, blocks, vols, out, ncoeff, numtypes, bzeroflag, b2j, 
     print("single_%s" % tag, [o[0].shape for o in out][:3])
 
 
+def group_weights():
+    """(eweight, fweight, vweight) tables of the reference's WBe and InP examples ([GROUPS] of
+    examples/WBe_PRB2019/WBe-example.in and examples/InP_JPCA2020/InP-example.in): the row-weight distributions of
+    BASELINE configs[4] / configs[2], used by the -m gpu parity tests at those shapes."""
+    import configparser
+    import json
+    out = {}
+    for tag, rel in (("WBe", "examples/WBe_PRB2019/WBe-example.in"), ("InP", "examples/InP_JPCA2020/InP-example.in")):
+        cp = configparser.ConfigParser(inline_comment_prefixes=("#",))
+        cp.optionxform = str
+        cp.read(os.path.join(rd.REFERENCE_ROOT, rel))
+        rows = []
+        for name, val in cp["GROUPS"].items():
+            if name in ("group_sections", "group_types", "smartweights", "random_sampling", "BOLTZT"):
+                continue
+            f = val.split()
+            rows.append([name, float(f[2]), float(f[3]), float(f[4])])
+        out[tag] = rows
+        print(tag, len(rows), "groups")
+    with open(os.path.join(OUT, "group_weights.json"), "w") as f:
+        json.dump(out, f, indent=0)
+
+
 def main():
     import sys
     os.makedirs(OUT, exist_ok=True)
     assert rd.reference_available(), "needs the reference tree at %s" % rd.REFERENCE_ROOT
-    which = sys.argv[1:] or ["ta", "solve", "anl", "scatter", "single"]
+    which = sys.argv[1:] or ["ta", "solve", "anl", "scatter", "single", "groups"]
+    if "groups" in which:
+        group_weights()
     if "ta" in which:
         ta_linear()
     if "solve" in which:

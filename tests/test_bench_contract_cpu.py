@@ -14,7 +14,7 @@ def _run(args, **kw):
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1"])
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-sample-configs", "300"])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -25,6 +25,11 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["config"]["workload"].startswith("c2")
+    # the reference arm reports the SAME config object the CUDA arm prints for this workload and GPU count
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.make_config("c2", 1)
+    assert d["rows_per_step"] == 300 * 100 and "diag(blank2J)" in d["cpu_baseline"]["sample"]
 
 
 def test_reference_arm_runs_on_rank_zero_only():

@@ -614,13 +614,32 @@ def test_anl_dropin_matches_reference_fixture(engine, name, tmp_path, monkeypatc
     s.engine = engine
     monkeypatch.chdir(tmp_path)
     s.perform_fit(a=a, b=b, w=w)
-    # anl.py:41-44 inverts the Gram itself: its result moves by ~cond(G + nugget I) * eps when the Gram changes in
-    # the last bit (device summation order vs numpy's), so the tolerance follows the conditioning of the case
-    # ("zerocol": cond ~ 1e13 with nugget 1e-6; the CPU suite pins the same class bit-tight on the reference's Gram)
+    # anl.py:41-44 inverts the Gram itself (pinv): its result moves by ~cond(G + nugget I) * eps when the Gram changes
+    # in the last bit (device summation order vs numpy's) -- the reference's own answer moves by as much between two
+    # BLAS builds.  So the bar with the DEVICE Gram is that bound, computed here for the case at hand ...
+    G, c, _btb, _n = lf.gram(a, b, w, t)
+    k = a.shape[1]
+    cond = np.linalg.cond(G + float(g["cov_nugget"]) * np.eye(k))
+    bound = max(1e-9, 20.0 * cond * np.finfo(np.float64).eps)
     mr, l2, _ = lf.coeff_rel_err(s.fit, g["ref_mean"])
-    tol = 1e-8 if name == "well" else 2e-3
-    assert (mr if name == "well" else l2) < tol, (mr, l2)
-    assert np.max(np.abs(s.cov - g["ref_cov"])) < (1e-7 if name == "well" else 2e-3) * np.max(np.abs(g["ref_cov"]))
+    assert l2 < bound, (l2, bound, cond)
+    assert np.max(np.abs(s.cov - g["ref_cov"])) < max(1e-7, bound) * np.max(np.abs(g["ref_cov"]))
+    # ... and with the reference's own Gram handed to the same class (everything after the Gram: pinv, symmetrisation,
+    # sigma-hat from the device residual pass, covariance) the result is the fixture's to rounding
+    class OracleGram:
+        def __getattr__(self, name):
+            return getattr(engine, name)
+
+        def gram(self, A, B, W, T=None):
+            full = np.zeros((k + 1, k + 1))
+            full[:k, :k], full[:k, k], full[k, :k], full[k, k] = G, c, c, _btb
+            return engine.to_device(full)
+    s2 = ANL("ANL", pt, cfg)
+    s2.engine = OracleGram()
+    s2.save_files = False
+    s2.perform_fit(a=a, b=b, w=w)
+    assert lf.coeff_rel_err(s2.fit, g["ref_mean"])[1] < 1e-9
+    assert np.max(np.abs(s2.cov - g["ref_cov"])) < 1e-7 * np.max(np.abs(g["ref_cov"]))
     assert s.fit_sam.shape == (3, a.shape[1])
     assert np.array_equal(np.load(tmp_path / "mean.npy"), s.fit)
     assert np.load(tmp_path / "covariance.npy").shape == s.cov.shape

@@ -43,6 +43,67 @@ def main():
             ok = ok and good
             print("dist_parity world=%d case=%s alpha=%g gram=%s: max_rel=%.2e l2=%.2e identical_on_all_ranks=%s %s"
                   % (world, case, alpha, path, mr, l2, same, "OK" if good else "FAIL"), flush=True)
+    # ---- the mirror solver classes made sharded by distributed.attach (perform_fit + error analysis) ----
+    from types import SimpleNamespace
+    from fitsnap_b200 import distributed
+    from fitsnap_b200.solvers import RIDGE, SVD
+    a, b, w, t = synth_system(**SOLVE_CASES["ill"])
+    lo, hi = shard_rows(a.shape[0], world, rank)
+    rt = np.where(np.arange(a.shape[0]) % 5 == 0, "Energy", "Force")
+    for cls, alpha in ((SVD, 0.0), (RIDGE, 1e-6)):
+        pt = SimpleNamespace(_rank=rank, shared_arrays={},
+                             fitsnap_dict={"Testing": [bool(v) for v in t[lo:hi]], "Groups": ["g%d" % (i % 3) for i in range(lo, hi)],
+                                           "Row_Type": list(rt[lo:hi])})
+        cfg = SimpleNamespace(sections={"RIDGE": SimpleNamespace(alpha=alpha, local_solver=0)})
+        s = cls(cls.__name__, pt, cfg)
+        distributed.attach(s, engine=eng)
+        s.perform_fit(a=a[lo:hi], b=b[lo:hi], w=w[lo:hi], fs_dict=pt.fitsnap_dict)
+        errs = s.error_analysis_device(a=a[lo:hi], b=b[lo:hi], w=w[lo:hi], fs_dict=pt.fitsnap_dict)
+        xs = [None] * world
+        dist.all_gather_object(xs, s.fit)
+        ns = [None] * world
+        dist.all_gather_object(ns, int(errs["ncount"].sum()))
+        if rank == 0:
+            ref = lf.svd_fit(a, b, w, t) if alpha == 0.0 else lf.ridge_fit_exact(a, b, w, alpha, t)
+            mr = lf.coeff_rel_err(s.fit, ref)[0]
+            same = all(np.array_equal(xs[0], v) for v in xs)
+            # every row is counted once in the '*ALL' block and once in its group block, weighted and unweighted
+            rows_ok = all(v == ns[0] for v in ns) and int(errs.loc["*ALL"].loc["Unweighted"]["ncount"].sum()) == a.shape[0]
+            good = same and mr < 1e-10 and rows_ok
+            ok = ok and good
+            print("dist_parity world=%d solver=%s attach: max_rel=%.2e identical_on_all_ranks=%s error_rows_ok=%s %s"
+                  % (world, cls.__name__, mr, same, rows_ok, "OK" if good else "FAIL"), flush=True)
+
+    # ---- CUDA-graph replay of the sharded device-resident step (peer-window collective inside the graph) ----
+    comm = eng.comm_for(dist.group.WORLD)
+    info = comm.info()
+    if info["peer_windows"]:
+        from fitsnap_b200.pipeline import LinearFitPipeline
+        eng.set_gram_path("auto")
+        rng = np.random.default_rng(100 + rank)
+        nt, nc, ncfg, n = 2, 14, 300, 9
+        kraw, k = nt * nc, nt * nc + nt
+        raw = rng.standard_normal((ncfg * (7 + 3 * n), kraw + 1))
+        pipe = LinearFitPipeline(nt, nc, False, np.ones(k), alpha=1e-8, refine=2, group=dist.group.WORLD, engine=eng)
+        st = rng.standard_normal((ncfg, 3, 3))
+        batch = pipe.pack(raw, np.full(ncfg, n, dtype=np.int32), rng.uniform(50, 500, ncfg), rng.standard_normal(ncfg),
+                          rng.standard_normal(ncfg * n * 3), 0.5 * (st + st.transpose(0, 2, 1)), np.ones(ncfg), np.ones(ncfg),
+                          np.full(ncfg, 1e-4), rng.dirichlet(np.ones(nt), ncfg))
+        eager = pipe.fit_batch(batch).x.clone()
+        cap = pipe.capture(batch)
+        for _ in range(3):
+            xg = cap.replay().x.clone()
+        torch.cuda.synchronize()
+        xs = [torch.empty_like(xg) for _ in range(world)]
+        dist.all_gather(xs, xg)
+        if rank == 0:
+            good = bool(torch.equal(eager, xg)) and all(torch.equal(xs[0], v) for v in xs)
+            ok = ok and good
+            print("dist_parity world=%d cuda_graph_of_sharded_step: replay == eager and identical on all ranks: %s %s"
+                  % (world, good, "OK" if good else "FAIL"), flush=True)
+    if rank == 0:
+        print("dist_parity collective: peer_windows=%s peer_calls=%d nccl_calls=%d OK"
+              % (info["peer_windows"], comm.info()["peer_calls"], comm.info()["nccl_calls"]), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
