@@ -50,6 +50,7 @@ SIGNATURES = {
     "fsb_factor_solve": (c_int, [c_void_p, _P, c_int32, _P, c_int64, c_double, _P, _P, c_void_p]),
     "fsb_pinv_bytes": (c_size_t, [c_void_p, c_int32]),
     "fsb_pinv_factor": (c_int, [c_void_p, _P, c_int32, c_double, _P, c_size_t, _P, c_void_p]),
+    "fsb_pinv_factor_shifted": (c_int, [c_void_p, _P, c_int32, c_double, c_double, _P, c_size_t, _P, c_void_p]),
     "fsb_pinv_apply": (c_int, [c_void_p, _P, c_int32, _P, c_int64, _P, _P, c_void_p]),
     "fsb_lasso": (c_int, [c_void_p, _P, c_int32, c_int64, c_double, c_int32, c_double, _P, _P, c_void_p]),
     "fsb_residual_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int32]),

@@ -38,8 +38,8 @@ int fsb_launch_group_stats(const fsb_context* h, const double* A, int64_t lda, c
                            cudaStream_t s);
 
 size_t fsb_pinv_bytes_impl(int k);
-int fsb_launch_pinv_factor(const fsb_context* h, const double* gaug, int k, double rcond, void* buf, size_t bytes,
-                           int32_t* info, cudaStream_t s);
+int fsb_launch_pinv_factor(const fsb_context* h, const double* gaug, int k, double rcond, double shift, void* buf,
+                           size_t bytes, int32_t* info, cudaStream_t s);
 int fsb_launch_pinv_apply(const void* buf, int k, const double* rhs, int64_t rhs_stride, const double* x_in,
                           double* x_out, cudaStream_t s);
 
@@ -201,7 +201,14 @@ size_t fsb_pinv_bytes(fsb_handle_t h, int32_t k) {
 int fsb_pinv_factor(fsb_handle_t h, const double* gaug, int32_t k, double rcond, void* pinv, size_t pinv_bytes,
                     int32_t* info, void* stream) {
   if (!h || !gaug || k < 1 || k > FSB_MAX_K || !pinv || !info || !(rcond >= 0.0)) return FSB_ERR_INVALID_ARGUMENT;
-  return fsb_launch_pinv_factor(h, gaug, k, rcond, pinv, pinv_bytes, info, (cudaStream_t)stream);
+  return fsb_launch_pinv_factor(h, gaug, k, rcond, 0.0, pinv, pinv_bytes, info, (cudaStream_t)stream);
+}
+
+int fsb_pinv_factor_shifted(fsb_handle_t h, const double* gaug, int32_t k, double rcond, double alpha, void* pinv,
+                            size_t pinv_bytes, int32_t* info, void* stream) {
+  if (!h || !gaug || k < 1 || k > FSB_MAX_K || !pinv || !info || !(rcond >= 0.0) || !(alpha >= 0.0))
+    return FSB_ERR_INVALID_ARGUMENT;
+  return fsb_launch_pinv_factor(h, gaug, k, rcond, alpha, pinv, pinv_bytes, info, (cudaStream_t)stream);
 }
 
 int fsb_pinv_apply(fsb_handle_t h, const void* pinv, int32_t k, const double* rhs, int64_t rhs_stride,

@@ -112,9 +112,12 @@ __global__ void __launch_bounds__(1024) jacobi_eig_kernel(const double* __restri
   if (tid == 0) info[1] = sweeps;
 }
 
-// P = V diag(1/lambda_i | lambda_i > cut) V^T ;  cut = rcond * max lambda ; info[0] = numerical rank
+// P = V diag(1/(lambda_i + shift) | lambda_i > cut) V^T ;  cut = rcond * max lambda ; info[0] = numerical rank
+// shift = 0: the pseudo-inverse (minimum-norm least squares); shift = alpha > 0: the ridge inverse restricted to the
+// numerical range of G (the exact ridge solution has no component in the null space of G: there aw^T bw vanishes)
 __global__ void __launch_bounds__(256) pinv_build_kernel(const double* __restrict__ V, const double* __restrict__ lam,
-                                                         int k, double rcond, double* __restrict__ P, int32_t* info) {
+                                                         int k, double rcond, double shift, double* __restrict__ P,
+                                                         int32_t* info) {
   extern __shared__ double inv[];   // k
   __shared__ double s_max;
   if (threadIdx.x == 0) {
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(256) pinv_build_kernel(const double* __restric
   int rank = 0;
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     const bool keep = lam[i] > cut && lam[i] > 0.0;
-    inv[i] = keep ? 1.0 / lam[i] : 0.0;
+    inv[i] = keep ? 1.0 / (lam[i] + shift) : 0.0;
   }
   __syncthreads();
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -159,8 +162,8 @@ __global__ void __launch_bounds__(256) pinv_apply_kernel(const double* __restric
 
 size_t fsb_pinv_bytes_impl(int k) { return ((size_t)3 * k * k + k) * sizeof(double); }   // P | work | V | lambda
 
-int fsb_launch_pinv_factor(const fsb_context* h, const double* gaug, int k, double rcond, void* buf, size_t bytes,
-                           int32_t* info, cudaStream_t s) {
+int fsb_launch_pinv_factor(const fsb_context* h, const double* gaug, int k, double rcond, double shift, void* buf,
+                           size_t bytes, int32_t* info, cudaStream_t s) {
   if (bytes < fsb_pinv_bytes_impl(k)) return FSB_ERR_WORKSPACE_TOO_SMALL;
   double* P = (double*)buf;
   double* work = P + (size_t)k * k;
@@ -173,7 +176,7 @@ int fsb_launch_pinv_factor(const fsb_context* h, const double* gaug, int k, doub
   jacobi_eig_kernel<<<1, 1024, smem, s>>>(gaug, k, work, V, lam, 30, info);
   FSB_LAUNCH_CHECK("jacobi_eig_kernel");
   dim3 grid((unsigned)fsb_ceil_div(k, 256), (unsigned)k);
-  pinv_build_kernel<<<grid, 256, (size_t)k * sizeof(double), s>>>(V, lam, k, rcond, P, info);
+  pinv_build_kernel<<<grid, 256, (size_t)k * sizeof(double), s>>>(V, lam, k, rcond, shift, P, info);
   FSB_LAUNCH_CHECK("pinv_build_kernel");
   return FSB_OK;
 }

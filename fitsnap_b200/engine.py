@@ -247,16 +247,18 @@ class Engine:
                                               factor.alpha, _ptr(x_in), _ptr(x), self._stream()))
         return x
 
-    def pinv_factor(self, gaug, rcond=None):
-        """G^+ through a Jacobi eigendecomposition (minimum-norm fallback, see csrc/pinv.cu)."""
+    def pinv_factor(self, gaug, rcond=None, alpha=0.0):
+        """G^+ (alpha = 0) or the range-restricted ridge inverse (alpha > 0) through a Jacobi eigendecomposition
+        (rank-deficient fallback, see csrc/pinv.cu)."""
         k = gaug.shape[0] - 1
         if rcond is None:
             rcond = k * 2.220446049250313e-16
         nbytes = self.lib.fsb_pinv_bytes(self._h, k)
         buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         info = torch.zeros(2, dtype=torch.int32, device=self.device)
-        _cabi.check("fsb_pinv_factor", self.lib.fsb_pinv_factor(self._h, _ptr(gaug), k, float(rcond), _ptr(buf), nbytes,
-                                                                 _ptr(info), self._stream()))
+        _cabi.check("fsb_pinv_factor_shifted",
+                    self.lib.fsb_pinv_factor_shifted(self._h, _ptr(gaug), k, float(rcond), float(alpha), _ptr(buf),
+                                                     nbytes, _ptr(info), self._stream()))
         return PinvFactor(buf, info, k)
 
     def pinv_apply(self, pf, rhs, rhs_stride=1, x_in=None):
@@ -437,16 +439,12 @@ def fit_rows(engine, A, b, w, testing=None, alpha=0.0, refine=2, group=None, dia
 def fit_rows_min_norm(engine, A, b, w, testing, gaug, refine=3, group=None, rcond=None, alpha=0.0):
     """Eigenvalue-truncated solve for a numerically rank-deficient system.  alpha = 0: the minimum-norm least-squares
     solution (what gelsd returns, svd.py:54): x0 = G^+ c, then x += G^+ aw^T (bw - aw x).  alpha > 0: the ridge
-    solution through (G + alpha I)^+ (sklearn's Ridge falls back to an SVD-based solve when its Cholesky breaks
-    down), refinement rhs aw^T (bw - aw x) - alpha x.  The residual is streamed from A; `gaug` is the (already
+    solution through V diag(1/(lambda + alpha)) V^T over the numerical range of G (sklearn's Ridge falls back to an
+    SVD-based solve when its Cholesky breaks down), refinement rhs aw^T (bw - aw x) - alpha x.  The residual is streamed from A; `gaug` is the (already
     all-reduced) augmented Gram of `fit_rows`."""
     start = getattr(engine, "launch_count", 0)
     k = gaug.shape[0] - 1
-    gsolve = gaug
-    if alpha:
-        gsolve = gaug.clone()
-        gsolve.diagonal()[:k].add_(float(alpha))
-    pf = engine.pinv_factor(gsolve, rcond)
+    pf = engine.pinv_factor(gaug, rcond, alpha=alpha)
     x = engine.pinv_apply(pf, gaug[:, k], rhs_stride=k + 1)
     last = None
     for _ in range(int(refine)):

@@ -198,6 +198,12 @@ int fsb_factor_solve(fsb_handle_t h, const void* factor, int32_t k, const double
 size_t fsb_pinv_bytes(fsb_handle_t h, int32_t k);
 int fsb_pinv_factor(fsb_handle_t h, const double* gaug, int32_t k, double rcond, void* pinv,
                     size_t pinv_bytes, int32_t* info, void* stream);
+/* ridge on a numerically rank-deficient system (sklearn's Ridge falls back from Cholesky to an SVD solve there,
+ * solvers/ridge.py:49-57): P = V diag(1/(lambda_i + alpha) | lambda_i > rcond * lambda_max) V^T -- the exact ridge
+ * solution has no component in the null space of G, so those directions are dropped rather than divided by alpha.
+ * Refinement: x_out = x_in + P (fsb_residual output - alpha * x_in). */
+int fsb_pinv_factor_shifted(fsb_handle_t h, const double* gaug, int32_t k, double rcond, double alpha, void* pinv,
+                            size_t pinv_bytes, int32_t* info, void* stream);
 int fsb_pinv_apply(fsb_handle_t h, const void* pinv, int32_t k, const double* rhs, int64_t rhs_stride,
                    const double* x_in, double* x_out, void* stream);
 
