@@ -365,6 +365,8 @@ def run_workload(eng, name, rank, world, group, steps, warmup, full, args, peaks
 
     for _ in range(warmup):
         res = pipe.fit_batch(batch, None, out)
+    fused = (not args.no_fused) and eng.scatter_gram(batch, *out) is not None     # narrow layouts: K1 + K2..K4 in one kernel
+    pipe.fuse_scatter_gram = fused
     torch.cuda.synchronize()
     barrier()
     sampler = ClockSampler(dev.index) if (rank == 0 and full) else None
@@ -377,9 +379,13 @@ def run_workload(eng, name, rank, world, group, steps, warmup, full, args, peaks
         # the step, with CUDA events between its phases on the stream the kernels are launched on
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record()
-        Ad, bd, wd, _bad = eng.scatter(batch, *out)
-        ev[1].record()
-        gaug = eng.gram(Ad, bd, wd, None)
+        if fused:
+            Ad, bd, wd, _bad, gaug = eng.scatter_gram(batch, *out)
+            ev[1].record()
+        else:
+            Ad, bd, wd, _bad = eng.scatter(batch, *out)
+            ev[1].record()
+            gaug = eng.gram(Ad, bd, wd, None)
         ev[2].record()
         allreduce(gaug)
         f = eng.factor(gaug, ALPHA)
@@ -400,9 +406,15 @@ def run_workload(eng, name, rank, world, group, steps, warmup, full, args, peaks
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     ms_step = float(t.item())
-    gram_ms = float(np.mean([ev[1].elapsed_time(ev[2]) for ev in phase_ev]))
-    names = ("scatter", "gram", "allreduce_factor_solve", "refine_%dx(residual+allreduce+solve)" % REFINE)
-    phases_ms = {nm: float(np.mean([ev[i].elapsed_time(ev[i + 1]) for ev in phase_ev])) for i, nm in enumerate(names)}
+    mean_ms = lambda i, j: float(np.mean([ev[i].elapsed_time(ev[j]) for ev in phase_ev]))
+    if fused:
+        gram_ms = mean_ms(0, 2)
+        phases_ms = {"scatter+gram (one fused kernel + split-K reduction)": gram_ms}
+    else:
+        gram_ms = mean_ms(1, 2)
+        phases_ms = {"scatter": mean_ms(0, 1), "gram": gram_ms}
+    phases_ms["allreduce_factor_solve"] = mean_ms(2, 3)
+    phases_ms["refine_%dx(residual+allreduce+solve)" % REFINE] = mean_ms(3, 4)
     value = world * n_rows / (ms_step / 1e3)
     x_dev = x.detach().cpu().numpy()
     gram_path = eng.gram_path(n_rows, k)
@@ -469,9 +481,13 @@ def run_workload(eng, name, rank, world, group, steps, warmup, full, args, peaks
                 "frac": achieved / bf16_peak, "traffic": None,
                 "peak_kind": "dense bf16 cuBLAS, %s (MEASURED_PEAKS.json)" % peak_kind,
                 "achieved_kind": "algorithmic fp64 flops (2k^2+2k per row, full Gram convention) / Gram time",
-                "hbm_gbs_during_gram": 8.0 * (k + 2) * n_rows / (gram_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak}
+                "hbm_gbs_during_gram": (16.0 * k + 24.0 if fused else 8.0 * (k + 2)) * n_rows / (gram_ms * 1e-3) / 1e9,
+                "hbm_peak_gbs": hbm_peak}
+    if fused:
+        roofline["fused_note"] = ("scatter_gram_kernel: the raw blocks are scattered into A, b, w AND contracted in the "
+                                  "same kernel; its time covers both (algorithmic bytes 16k+24 per row)")
     try:    # ncu-measured DRAM bytes per launch of the dominant kernel, when a capture of this shape is committed
-        tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("%s:%s" % (name, gram_path))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("%s:%s" % (name, "fused" if fused else gram_path))
         if tr:
             roofline["traffic"] = tr["bytes_per_launch"]
             roofline["traffic_note"] = "%s, %d rows x %d: %.3g B from ncu vs %.3g B algorithmic (%s)" % (
@@ -494,7 +510,7 @@ def run_workload(eng, name, rank, world, group, steps, warmup, full, args, peaks
             "fp64_equivalent_tflops": achieved})
     else:
         roofline.update({
-            "kernel": ("gram_rowsplit_kernel" if k + 1 <= 104 else
+            "kernel": ("scatter_gram_kernel" if fused else "gram_rowsplit_kernel" if k + 1 <= 104 else
                        ("gram_dmma_kernel" if k + 1 <= 128 else "preweight_kernel + gram_tma_kernel")) +
                       " (+gram_reduce_kernel)",
             "frac_of_fp64_dmma_peak": achieved / 37.1,
@@ -506,8 +522,10 @@ def run_workload(eng, name, rank, world, group, steps, warmup, full, args, peaks
         "config": make_config(name, world, gram_path),
         "gram_ms": gram_ms, "gram_tflops_algorithmic": achieved,
         "phases_ms_rank0": phases_ms,
-        "scatter_GBps": (16.0 * k + 24.0) * n_rows / (phases_ms["scatter"] * 1e-3) / 1e9,
-        "scatter_frac_of_hbm_peak": (16.0 * k + 24.0) * n_rows / (phases_ms["scatter"] * 1e-3) / 1e9 / hbm_peak,
+        "scatter_GBps": None if fused else (16.0 * k + 24.0) * n_rows / (phases_ms["scatter"] * 1e-3) / 1e9,
+        "scatter_frac_of_hbm_peak": None if fused else
+        (16.0 * k + 24.0) * n_rows / (phases_ms["scatter"] * 1e-3) / 1e9 / hbm_peak,
+        "fused_scatter_gram": bool(fused),
         "roofline": roofline, "coeff_max_rel_err": coeff_err, "gpu_launches": int(launches),
         "cuda_graph_replay": graph_info,
         "collective": comm.info() if comm is not None else None,
@@ -529,6 +547,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="scatter and Gram as two kernels even for narrow layouts")
     ap.add_argument("--graph-all", action="store_true", help="CUDA-graph replay for the secondary workload too")
     ap.add_argument("--ref-sample-configs", type=int, default=0, help="reference arm: cap the configurations per step")
     args = ap.parse_args()

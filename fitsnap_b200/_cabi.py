@@ -41,6 +41,10 @@ SIGNATURES = {
     "fsb_comm_destroy": (c_int, [c_void_p]),
     "fsb_scatter": (c_int, [c_void_p, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                             c_int32, c_int32, c_int32, c_int32, _P, c_int64, _P, _P, c_int64, _P, _P, c_void_p]),
+    "fsb_row_map": (c_int, [c_void_p, _P, c_int32, _P, c_int64, c_void_p]),
+    "fsb_scatter_gram": (c_int, [c_void_p, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                 c_int32, c_int32, c_int32, c_int32, _P, c_int64, _P, _P, c_int64, _P, _P, _P, _P, _P,
+                                 c_size_t, c_void_p]),
     "fsb_set_gram_path": (c_int, [c_void_p, c_int32]),
     "fsb_get_gram_path": (c_int, [c_void_p, c_int64, c_int32, POINTER(c_int32)]),
     "fsb_gram_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int32]),
@@ -62,6 +66,9 @@ SIGNATURES = {
 
 class NativeLibraryError(RuntimeError):
     """libfitsnap_b200.so is missing or lacks a declared symbol."""
+
+
+UNSUPPORTED = 4
 
 
 class FsbError(RuntimeError):

@@ -140,10 +140,15 @@ def pack_configs(engine, blocks, natoms, volumes, energies, forces, stresses, ew
                 type_fraction=tf, blank2j=b2j)
     dev = {name: up(arr) for name, arr in host.items()}
     dev["raw"] = raw_dev
-    # row -> configuration map: left to the kernel (binary search in out_row_off), nothing to upload
     nbytes = raw.nbytes + sum(a.nbytes for a in host.values()) + raw_off.nbytes + out_off.nbytes + natoms.nbytes
-    return ConfigBatch(raw_row_off=up(raw_off, dtype=torch.int64), out_row_off=up(out_off, dtype=torch.int64),
+    out_off_dev = up(out_off, dtype=torch.int64)
+    # row -> configuration map, built on the device (nothing to upload): it lets the scatter take its TMA-staged
+    # kernel and, for narrow matrices, the fused scatter + Gram kernel
+    row_cfg = None
+    if ncfg and hasattr(engine, "row_map"):
+        row_cfg = engine.row_map(out_off_dev, ncfg, int(out_off[-1] - out_off[0]))
+    return ConfigBatch(raw_row_off=up(raw_off, dtype=torch.int64), out_row_off=out_off_dev,
                        natoms=up(natoms, dtype=torch.int32), ncfg=ncfg, numtypes=int(numtypes), ncoeff=int(ncoeff),
                        flags=make_flags(energy, force, stress, bzeroflag, scrub_nonfinite), k=k,
-                       row_begin=int(out_off[0]), row_end=int(out_off[-1]), row_cfg=None,
+                       row_begin=int(out_off[0]), row_end=int(out_off[-1]), row_cfg=row_cfg,
                        h2d_bytes=int(nbytes), **dev)

@@ -27,6 +27,9 @@ int fsb_launch_scatter(const fsb_context* h, const double* raw, const int64_t* r
                        int ncoeff, int flags, double* A, int64_t lda, double* b, double* w,
                        int32_t* nonfinite, const int32_t* row_cfg, int64_t n_rows_hint, cudaStream_t s);
 
+int fsb_launch_scatter_gram(const fsb_context* h, const ScatterArgs& sc, const uint8_t* testing, int64_t total,
+                            int store_a, double* gaug, void* ws, size_t ws_bytes, cudaStream_t s);
+int fsb_launch_row_map(const int64_t* out_row_off, int ncfg, int32_t* row_cfg, int64_t n_rows, cudaStream_t s);
 bool fsb_gram_i8_available();
 int fsb_gram_path_for(const fsb_context* h, int64_t n_rows, int k);
 
@@ -144,6 +147,40 @@ int fsb_scatter(fsb_handle_t h, const double* raw, const int64_t* raw_row_off, c
   return fsb_launch_scatter(h, raw, raw_row_off, out_row_off, natoms, volume, energy, forces, stress, eweight,
                             fweight, vweight, type_fraction, blank2j, ncfg, numtypes, ncoeff, flags, A, lda, b,
                             w, nonfinite, row_cfg, n_rows_out, (cudaStream_t)stream);
+}
+
+int fsb_row_map(fsb_handle_t h, const int64_t* out_row_off, int32_t ncfg, int32_t* row_cfg, int64_t n_rows_out,
+                void* stream) {
+  if (!h || ncfg < 0 || n_rows_out < 0) return FSB_ERR_INVALID_ARGUMENT;
+  if (ncfg == 0 || n_rows_out == 0) return FSB_OK;
+  if (!out_row_off || !row_cfg) return FSB_ERR_INVALID_ARGUMENT;
+  return fsb_launch_row_map(out_row_off, ncfg, row_cfg, n_rows_out, (cudaStream_t)stream);
+}
+
+int fsb_scatter_gram(fsb_handle_t h, const double* raw, const int64_t* raw_row_off, const int64_t* out_row_off,
+                     const int32_t* natoms, const double* volume, const double* energy, const double* forces,
+                     const double* stress, const double* eweight, const double* fweight, const double* vweight,
+                     const double* type_fraction, const double* blank2j, int32_t ncfg, int32_t numtypes,
+                     int32_t ncoeff, int32_t flags, double* A, int64_t lda, double* b, double* w, int64_t n_rows_out,
+                     const int32_t* row_cfg, int32_t* nonfinite, const uint8_t* testing, double* gaug, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  if (!h || ncfg < 1 || numtypes < 1 || ncoeff < 1 || n_rows_out < 1 || !gaug || !workspace)
+    return FSB_ERR_INVALID_ARGUMENT;
+  if (!raw || !raw_row_off || !out_row_off || !natoms || !blank2j || !b || !w || !row_cfg)
+    return FSB_ERR_INVALID_ARGUMENT;
+  const bool bzero = flags & FSB_BZEROFLAG;
+  const int k = ncoeff * numtypes + (bzero ? 0 : numtypes);
+  if (A && lda < k) return FSB_ERR_INVALID_ARGUMENT;
+  if (!energy || !eweight || (!bzero && !type_fraction) || !forces || !fweight || !stress || !vweight || !volume)
+    return FSB_ERR_INVALID_ARGUMENT;
+  ScatterArgs a;
+  a.raw = raw; a.raw_row_off = raw_row_off; a.out_row_off = out_row_off; a.natoms = natoms;
+  a.volume = volume; a.energy = energy; a.forces = forces; a.stress = stress;
+  a.eweight = eweight; a.fweight = fweight; a.vweight = vweight; a.type_fraction = type_fraction;
+  a.blank2j = blank2j; a.ncfg = ncfg; a.numtypes = numtypes; a.ncoeff = ncoeff; a.flags = flags;
+  a.A = A; a.lda = A ? lda : k; a.b = b; a.w = w; a.nonfinite = nonfinite; a.row_cfg = row_cfg;
+  return fsb_launch_scatter_gram(h, a, testing, n_rows_out, A ? 1 : 0, gaug, workspace, workspace_bytes,
+                                 (cudaStream_t)stream);
 }
 
 int fsb_set_gram_path(fsb_handle_t h, int32_t path) {

@@ -61,3 +61,44 @@ int fsb_launch_gram(const fsb_context* h, const double* A, int64_t lda, const do
                     const uint8_t* testing, int64_t n_rows, int k, double* gaug, void* ws, size_t ws_bytes,
                     cudaStream_t s);
 size_t fsb_gram_ws_bytes(const fsb_context* h, int64_t n_rows, int k);
+
+// ---- K1 arguments (stream_ops.cu: scatter kernels; gram_small.cu: fused scatter + Gram) -----------------
+struct ScatterArgs {
+  const double* raw;
+  const int64_t* raw_row_off;
+  const int64_t* out_row_off;
+  const int32_t* natoms;
+  const double* volume;
+  const double* energy;
+  const double* forces;
+  const double* stress;
+  const double* eweight;
+  const double* fweight;
+  const double* vweight;
+  const double* type_fraction;
+  const double* blank2j;
+  int ncfg, numtypes, ncoeff, flags;
+  double* A;
+  int64_t lda;
+  double* b;
+  double* w;
+  int32_t* nonfinite;
+  const int32_t* row_cfg;   // optional: configuration index of every output row
+};
+
+constexpr double FSB_VIRIAL_UNIT = 1.6021765e6;  // lammps_snap.py:526
+
+#ifdef __CUDACC__
+namespace fsb_dev {
+__device__ __forceinline__ double scrub(double v, bool do_scrub, bool& bad) {
+  if (!isfinite(v)) {
+    bad = true;
+    if (do_scrub) {  // numpy.nan_to_num defaults (lammps_pace.py:401)
+      if (isnan(v)) return 0.0;
+      return v > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    }
+  }
+  return v;
+}
+}  // namespace fsb_dev
+#endif

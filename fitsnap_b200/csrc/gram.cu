@@ -357,6 +357,28 @@ static size_t partial_bytes(const GramPlan& pl) {
   return (size_t)pl.nchunk * pl.ntile * FSB_GT * FSB_GT * sizeof(double);
 }
 
+// fused K1 + K2..K4 for narrow matrices (gram_small.cu: scatter_gram_kernel) + the deterministic split-K reduction
+bool fsb_scatter_gram_supported(const ScatterArgs& sc, int64_t total);
+int fsb_launch_scatter_gram_small(const fsb_context* h, const ScatterArgs& sc, const uint8_t* testing, int64_t total,
+                                  int store_a, double* partial, cudaStream_t s);
+
+int fsb_launch_scatter_gram(const fsb_context* h, const ScatterArgs& sc, const uint8_t* testing, int64_t total,
+                            int store_a, double* gaug, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (!fsb_scatter_gram_supported(sc, total)) return FSB_ERR_UNSUPPORTED;
+  const bool bzero = sc.flags & FSB_BZEROFLAG;
+  const int k = sc.ncoeff * sc.numtypes + (bzero ? 0 : sc.numtypes);
+  if (fsb_gram_path_for(h, total, k) != FSB_GRAM_FP64 || !use_small(k)) return FSB_ERR_UNSUPPORTED;
+  GramPlan pl = effective_plan(h, total, k);
+  if (ws_bytes < align256(partial_bytes(pl))) return FSB_ERR_WORKSPACE_TOO_SMALL;
+  int st = fsb_launch_scatter_gram_small(h, sc, testing, total, store_a, (double*)ws, s);
+  if (st != FSB_OK) return st;
+  const int ka = k + 1;
+  dim3 rgrid((unsigned)fsb_ceil_div(ka, 32), (unsigned)ka);
+  gram_reduce_kernel<<<rgrid, 256, 0, s>>>((const double*)ws, pl.nchunk, 1, ka, gaug);
+  FSB_LAUNCH_CHECK("gram_reduce_kernel");
+  return FSB_OK;
+}
+
 size_t fsb_gram_ws_bytes(const fsb_context* h, int64_t n_rows, int k) {
   if (fsb_gram_path_for(h, n_rows, k) == FSB_GRAM_INT8)
     return align256((size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double)) + fsb_gram_i8_ws_bytes(n_rows, k);

@@ -21,6 +21,7 @@
 //  * each consumer group writes its partial Gram as one split-K "chunk"; gram_reduce_kernel
 //    (gram.cu) sums the chunks in a fixed order (deterministic).
 #include "fsb_common.cuh"
+#include <limits.h>
 #include <stdlib.h>
 
 namespace {
@@ -74,7 +75,7 @@ __device__ __forceinline__ void bar_arrive(int id, int count) {
 }
 
 template <int R0, int R1>
-__device__ __forceinline__ void consume(const SmallArgs& p, const double* smem, int pitch, int nstage, int group,
+__device__ __forceinline__ void consume(double* partial, const double* smem, int pitch, int nstage, int group,
                                         int lane, int nsteps, int64_t cta) {
   constexpr int NACC = (R1 * (R1 + 1) - R0 * (R0 + 1)) / 2 > 0 ? (R1 * (R1 + 1) - R0 * (R0 + 1)) / 2 : 1;
   constexpr int base = R0 * (R0 + 1) / 2;
@@ -108,7 +109,7 @@ __device__ __forceinline__ void consume(const SmallArgs& p, const double* smem, 
     }
     if (s + nstage < nsteps) bar_arrive(1 + S_MAXSTAGE + slot, S_THREADS);   // EMPTY[slot]
   }
-  double* out = p.partial + ((size_t)cta * S_GROUPS + group) * (size_t)(FSB_GT * FSB_GT);
+  double* out = partial + ((size_t)cta * S_GROUPS + group) * (size_t)(FSB_GT * FSB_GT);
 #pragma unroll
   for (int i = R0; i < R1; ++i)
 #pragma unroll
@@ -252,11 +253,229 @@ __global__ void __launch_bounds__(S_THREADS, 1) gram_rowsplit_kernel(SmallArgs p
   const int part = (group == 0) ? (warp & 3) : 3 - (warp & 3);   // reversed in group 1: schedulers balanced
   constexpr int B1 = part_begin(NB, 1), B2 = part_begin(NB, 2), B3 = part_begin(NB, 3);
   switch (part) {
-    case 0: consume<0, B1>(p, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
-    case 1: consume<B1, B2>(p, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
-    case 2: consume<B2, B3>(p, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
-    default: consume<B3, NB>(p, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
+    case 0: consume<0, B1>(p.partial, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
+    case 1: consume<B1, B2>(p.partial, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
+    case 2: consume<B2, B3>(p.partial, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
+    default: consume<B3, NB>(p.partial, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K2..K4 FUSED: raw LAMMPS blocks -> rows of A, b, w (written once, for the refinement passes; or not at all)
+// AND, from the same registers, the weighted rows that feed the DMMA consumers.  The design matrix is never read
+// back for the Gram: the scatter's HBM traffic (16k + 24 bytes per row) hides behind the fp64 tensor work, which is
+// the longer of the two (this is the per-batch `C += aw^T aw; d += aw^T bw` of
+// examples/library/transpose_trick/example.py:226-246, with `_collect_lammps` (lammps_snap.py:391-556) fused in).
+//
+// Same CTA shape as gram_rowsplit_kernel: 8 consumer warps (identical code: the Gram is bit-identical to
+// scatter -> gram_rowsplit on the same rows) + 4 producer warps.  Producer thread c owns column c of the augmented
+// matrix [A | b]: per half stage it loads its raw column for 16 rows (coalesced across the warp: raw columns are
+// contiguous), applies the row's transform (/N, *1.6021765e6/V, type fraction, blank2J -- the operations of
+// scatter_kernel in the same order, bit-identical A, b, w), stores A (coalesced) and the weighted value into the
+// ring.  Row metadata (row -> configuration -> kind / divisor / weight / truth) is a chain of dependent global
+// loads: lane r of every producer warp resolves row r of a stage, three stages ahead of its use, one level of the
+// chain per stage, and the store loop broadcasts it with shuffles.
+// Requirements: energy + force + virial rows all assembled (raw row i <-> output row i), row_cfg given,
+// k + 1 <= 104.  Anything else takes the two separate kernels.
+struct FusedArgs {
+  ScatterArgs sc;
+  const uint8_t* testing;   // optional test mask of the output rows of this call (1 = excluded from the Gram)
+  int64_t total;            // rows of this call
+  int64_t rows_per_cta;
+  double* partial;
+  int store_a;              // 0: streaming mode, A is not materialised (b and w still are)
+};
+
+struct FusedM2 {            // second level of the metadata chain (lane = row)
+  int cfg, nat;
+  unsigned tst;
+  int64_t off;
+  double ew, fw, vw, en, vol, fo;
+};
+struct FusedRow {           // resolved row (lane = row)
+  double div, wv, truth, wg;   // wg: weight seen by the Gram (0 for test rows and rows past the end)
+  int kind, cfg;               // kind: 0 energy, 1 force, 2 virial, -1 past the end
+};
+
+template <int NB>
+__global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p) {
+  extern __shared__ double smem[];   // [NSTAGE][S_RCH x PITCH]
+  constexpr int PITCH = 8 * NB + 4;
+  constexpr int NSTAGE = ring_depth(NB);
+  constexpr int KP = 8 * NB;
+  constexpr int HALF = S_RCH / 2;
+  const ScatterArgs& a = p.sc;
+  const bool bzero = a.flags & FSB_BZEROFLAG, do_scrub = a.flags & FSB_SCRUB_NONFINITE;
+  const int kraw = a.ncoeff * a.numtypes;
+  const int k = bzero ? kraw : kraw + a.numtypes;
+  const int seg = a.ncoeff + 1;
+  const int64_t ldr = kraw + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t cta = blockIdx.x;
+  const int64_t row_begin = cta * p.rows_per_cta;
+  int64_t row_end = row_begin + p.rows_per_cta;
+  if (row_end > p.total) row_end = p.total;
+  const int nsteps = row_end > row_begin ? (int)((row_end - row_begin + S_RCH - 1) / S_RCH) : 0;
+
+  if (warp >= S_CONSUMERS / 32) {
+    const int c = tid - S_CONSUMERS;          // column of the augmented matrix owned by this thread
+    int srcc = INT_MIN;                       // >= 0: raw column; < 0: lead column of type (-v-1); INT_MIN: padding
+    double pref = 0.0;
+    if (c < k) {
+      int v = c;
+      if (!bzero) {
+        const int t = c / seg, q = c - t * seg;
+        v = (q == 0) ? -(t + 1) : t * a.ncoeff + q - 1;
+      }
+      srcc = v;
+      pref = __ldg(a.blank2j + c);
+    } else if (c == k) {
+      srcc = kraw;                            // reference-potential column
+    }
+    const int64_t row0 = a.out_row_off[0], rraw0 = a.raw_row_off[0];
+    const int64_t n_force = p.total - 7 * (int64_t)a.ncfg > 1 ? p.total - 7 * (int64_t)a.ncfg : 1;   // 3 * atoms
+    const double* rawc = a.raw + rraw0 * ldr + (srcc >= 0 ? srcc : 0);
+    const bool loads_raw = srcc >= 0;
+    bool bad = false;
+
+    auto level1 = [&](int s, int& cfg, unsigned& tst) {
+      const int64_t i = row_begin + (int64_t)s * S_RCH + lane;
+      cfg = -1;
+      tst = 0u;
+      if (s < nsteps && i < row_end) {
+        cfg = __ldg(a.row_cfg + i);
+        if (p.testing) tst = (unsigned)__ldg(p.testing + i);
+      }
+    };
+    auto level2 = [&](int s, int cfg, unsigned tst, FusedM2& m) {
+      m.cfg = cfg; m.tst = tst; m.nat = 1; m.off = 0;
+      m.ew = m.fw = m.vw = m.en = m.vol = m.fo = 0.0;
+      if (cfg >= 0) {
+        const int64_t i = row_begin + (int64_t)s * S_RCH + lane;
+        int64_t fi = i - 7 * (int64_t)cfg - 1;                 // rows map 1:1 (see scatter_bulk_kernel)
+        fi = fi < 0 ? 0 : (fi > n_force - 1 ? n_force - 1 : fi);
+        m.nat = __ldg(a.natoms + cfg);
+        m.off = __ldg(a.out_row_off + cfg);
+        m.ew = __ldg(a.eweight + cfg); m.fw = __ldg(a.fweight + cfg); m.vw = __ldg(a.vweight + cfg);
+        m.en = __ldg(a.energy + cfg); m.vol = __ldg(a.volume + cfg); m.fo = __ldg(a.forces + fi);
+      }
+    };
+    auto level3 = [&](int s, const FusedM2& m, FusedRow& r) {
+      r.kind = -1; r.cfg = 0; r.div = 1.0; r.wv = 0.0; r.truth = 0.0; r.wg = 0.0;
+      if (m.cfg >= 0) {
+        const int64_t i = row_begin + (int64_t)s * S_RCH + lane;
+        const int64_t local = row0 + i - m.off;
+        r.cfg = m.cfg;
+        if (local == 0) {
+          r.kind = 0; r.div = (double)m.nat; r.wv = m.ew; r.truth = m.en;
+          if (!bzero) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.type_fraction + (size_t)m.cfg * a.numtypes));
+        } else if (local < 1 + 3 * (int64_t)m.nat) {
+          r.kind = 1; r.wv = m.fw; r.truth = m.fo;
+        } else {
+          const int sub = (int)(local - 1 - 3 * (int64_t)m.nat);
+          const int vi[6] = {0, 1, 2, 1, 0, 0}, vj[6] = {0, 1, 2, 2, 2, 1};
+          r.kind = 2; r.div = m.vol; r.wv = m.vw;
+          r.truth = __ldg(a.stress + (size_t)m.cfg * 9 + vi[sub] * 3 + vj[sub]);
+        }
+        r.wg = m.tst ? 0.0 : r.wv;
+      }
+    };
+    auto load_half = [&](int h, double (&v)[HALF]) {
+      const int64_t i0 = row_begin + (int64_t)h * HALF;
+#pragma unroll
+      for (int j = 0; j < HALF; ++j) {
+        const int64_t i = i0 + j;
+        const int64_t ic = i < row_end ? i : row_end - 1;        // clamped; rows past the end are not used
+        v[j] = loads_raw ? __ldg(rawc + ic * ldr) : 0.0;
+      }
+    };
+    auto store_half = [&](int h, const double (&v)[HALF], const FusedRow& r) {
+      const int s = h >> 1;
+      const int slot = s % NSTAGE;
+      double* st = smem + (size_t)slot * (S_RCH * PITCH) + c;
+      const int64_t i0 = row_begin + (int64_t)h * HALF;
+#pragma unroll
+      for (int j = 0; j < HALF; ++j) {
+        const int rr = (h & 1) * HALF + j;
+        const int kind = __shfl_sync(0xffffffffu, r.kind, rr);
+        const double div = __shfl_sync(0xffffffffu, r.div, rr);
+        const double wg = __shfl_sync(0xffffffffu, r.wg, rr);
+        const double wv = __shfl_sync(0xffffffffu, r.wv, rr);
+        const double truth = __shfl_sync(0xffffffffu, r.truth, rr);
+        const int cfg = __shfl_sync(0xffffffffu, r.cfg, rr);
+        double out = 0.0;
+        if (kind >= 0 && c <= k) {
+          const int64_t orow = row0 + i0 + j;
+          double x = v[j];
+          if (loads_raw && (((unsigned)__double2hiint(x) & 0x7ff00000u) == 0x7ff00000u)) x = fsb_dev::scrub(x, do_scrub, bad);
+          if (c < k) {
+            double val;
+            if (kind == 1) val = (loads_raw ? x : 0.0) * pref;                                  // lammps_snap.py:493-502
+            else if (kind == 2) val = (loads_raw ? (FSB_VIRIAL_UNIT * x) / div : 0.0) * pref;   // :526-536
+            else val = (loads_raw ? x / div
+                                  : __ldg(a.type_fraction + (size_t)cfg * a.numtypes + (-srcc - 1))) * pref;   // :435-467
+            if (p.store_a) a.A[orow * a.lda + c] = val;
+            out = val * wg;                                                                     // fl(w*a) (svd.py:44)
+          } else {
+            const double bv = (kind == 0) ? (truth - x) / div : truth - x;                      // :473, :506-507, :540-541
+            a.b[orow] = bv;
+            a.w[orow] = wv;
+            out = bv * wg;
+          }
+        }
+        if (c < KP) st[rr * PITCH] = out;
+      }
+    };
+
+    // metadata pipeline: cfg of stage s+3, level 2 of stage s+2, level 3 of stage s+1 are issued while stage s is stored
+    int cfg1 = -1, cfg2 = -1, cfgN = -1;
+    unsigned tst1 = 0u, tst2 = 0u, tstN = 0u;
+    FusedM2 m2a, m2b;
+    FusedRow rowA, rowB;
+    level1(0, cfg1, tst1);
+    level2(0, cfg1, tst1, m2a);
+    level3(0, m2a, rowA);                 // stage 0 ready
+    level1(1, cfg1, tst1);
+    level2(1, cfg1, tst1, m2a);           // stage 1: level 2 in flight
+    level1(2, cfg2, tst2);                // stage 2: level 1 in flight
+    double va[HALF], vb[HALF];
+    if (nsteps > 0) load_half(0, va);
+    for (int s = 0; s < nsteps; ++s) {
+      level1(s + 3, cfgN, tstN);
+      level2(s + 2, cfg2, tst2, m2b);
+      level3(s + 1, m2a, rowB);
+      load_half(2 * s + 1, vb);
+      if (s >= NSTAGE) bar_sync(1 + S_MAXSTAGE + (s % NSTAGE), S_THREADS);   // EMPTY[slot]
+      store_half(2 * s, va, rowA);
+      if (s + 1 < nsteps) load_half(2 * s + 2, va);
+      store_half(2 * s + 1, vb, rowA);
+      __threadfence_block();
+      bar_arrive(1 + (s % NSTAGE), S_THREADS);                               // FULL[slot]
+      rowA = rowB; m2a = m2b; cfg2 = cfgN; tst2 = tstN;
+    }
+    if (a.nonfinite && __any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(a.nonfinite, 1);
+    return;
+  }
+
+  const int group = warp >> 2;
+  const int part = (group == 0) ? (warp & 3) : 3 - (warp & 3);
+  constexpr int B1 = part_begin(NB, 1), B2 = part_begin(NB, 2), B3 = part_begin(NB, 3);
+  switch (part) {
+    case 0: consume<0, B1>(p.partial, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
+    case 1: consume<B1, B2>(p.partial, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
+    case 2: consume<B2, B3>(p.partial, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
+    default: consume<B3, NB>(p.partial, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
+  }
+}
+
+template <int NB>
+int launch_fused_nb(const FusedArgs& a, int ncta, cudaStream_t s) {
+  constexpr int PITCH = 8 * NB + 4;
+  const size_t smem = (size_t)ring_depth(NB) * (S_RCH * PITCH) * sizeof(double);
+  FSB_CUDA_TRY(cudaFuncSetAttribute(scatter_gram_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  scatter_gram_kernel<NB><<<ncta, S_THREADS, smem, s>>>(a);
+  FSB_LAUNCH_CHECK("scatter_gram_kernel");
+  return FSB_OK;
 }
 
 template <int NB>
@@ -293,6 +512,34 @@ int fsb_launch_gram_small(const fsb_context* h, const double* A, int64_t lda, co
   // ones see an empty row range and write zeros
   switch (nb) {
 #define FSB_NB(N) case N: return launch_nb<N>(a, want, s);
+    FSB_NB(1) FSB_NB(2) FSB_NB(3) FSB_NB(4) FSB_NB(5) FSB_NB(6) FSB_NB(7)
+    FSB_NB(8) FSB_NB(9) FSB_NB(10) FSB_NB(11) FSB_NB(12) FSB_NB(13)
+#undef FSB_NB
+    default: return FSB_ERR_UNSUPPORTED;
+  }
+}
+
+// fused scatter + Gram (see scatter_gram_kernel); the caller reduces the split-K partials like the unfused path
+bool fsb_scatter_gram_supported(const ScatterArgs& sc, int64_t total) {
+  const int all_rows = FSB_ROWS_ENERGY | FSB_ROWS_FORCE | FSB_ROWS_STRESS;
+  const bool bzero = sc.flags & FSB_BZEROFLAG;
+  const int k = sc.ncoeff * sc.numtypes + (bzero ? 0 : sc.numtypes);
+  static int off = -1;
+  if (off < 0) off = getenv("FSB_NO_FUSED_SCATTER_GRAM") ? 1 : 0;
+  return !off && (sc.flags & all_rows) == all_rows && sc.row_cfg != nullptr && (k + 1 + 7) / 8 <= 13 && total > 0;
+}
+
+int fsb_launch_scatter_gram_small(const fsb_context* h, const ScatterArgs& sc, const uint8_t* testing, int64_t total,
+                                  int store_a, double* partial, cudaStream_t s) {
+  const bool bzero = sc.flags & FSB_BZEROFLAG;
+  const int k = sc.ncoeff * sc.numtypes + (bzero ? 0 : sc.numtypes);
+  const int nb = (k + 1 + 7) / 8;
+  FusedArgs a;
+  a.sc = sc; a.testing = testing; a.total = total; a.partial = partial; a.store_a = store_a;
+  const int want = fsb_gram_small_ctas(h, total);
+  a.rows_per_cta = fsb_round_up(fsb_ceil_div(total > 0 ? total : 1, want), S_RCH);
+  switch (nb) {
+#define FSB_NB(N) case N: return launch_fused_nb<N>(a, want, s);
     FSB_NB(1) FSB_NB(2) FSB_NB(3) FSB_NB(4) FSB_NB(5) FSB_NB(6) FSB_NB(7)
     FSB_NB(8) FSB_NB(9) FSB_NB(10) FSB_NB(11) FSB_NB(12) FSB_NB(13)
 #undef FSB_NB

@@ -488,39 +488,7 @@ int launch_rowpass(const fsb_context* h, const double* A, int64_t lda, const dou
 }
 
 // ------------------------------------------------------------------------------ K1
-struct ScatterArgs {
-  const double* raw;
-  const int64_t* raw_row_off;
-  const int64_t* out_row_off;
-  const int32_t* natoms;
-  const double* volume;
-  const double* energy;
-  const double* forces;
-  const double* stress;
-  const double* eweight;
-  const double* fweight;
-  const double* vweight;
-  const double* type_fraction;
-  const double* blank2j;
-  int ncfg, numtypes, ncoeff, flags;
-  double* A;
-  int64_t lda;
-  double* b;
-  double* w;
-  int32_t* nonfinite;
-  const int32_t* row_cfg;   // optional: configuration index of every output row
-};
-
-__device__ __forceinline__ double scrub(double v, bool do_scrub, bool& bad) {
-  if (!isfinite(v)) {
-    bad = true;
-    if (do_scrub) {  // numpy.nan_to_num defaults (lammps_pace.py:401)
-      if (isnan(v)) return 0.0;
-      return v > 0 ? DBL_MAX : -DBL_MAX;
-    }
-  }
-  return v;
-}
+using fsb_dev::scrub;
 
 // A CTA walks tiles of SC_TILE consecutive output rows.  Phase 1: one thread per row resolves the
 // row's metadata (configuration, row family, source row, divisor) with independent global loads and
@@ -916,7 +884,28 @@ __global__ void __launch_bounds__(SB_THREADS, 1) scatter_bulk_kernel(ScatterArgs
 }
 
 
+// row -> configuration map of a batch: row_cfg[i] = largest c with out_row_off[c] <= out_row_off[0] + i
+__global__ void __launch_bounds__(256) row_map_kernel(const int64_t* __restrict__ out_row_off, int ncfg,
+                                                      int32_t* __restrict__ row_cfg, int64_t n_rows) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const int64_t row = __ldg(out_row_off) + i;
+  int lo = 0, hi = ncfg - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(out_row_off + mid) <= row) lo = mid; else hi = mid - 1;
+  }
+  row_cfg[i] = lo;
+}
+
 }  // namespace
+
+int fsb_launch_row_map(const int64_t* out_row_off, int ncfg, int32_t* row_cfg, int64_t n_rows, cudaStream_t s) {
+  if (n_rows == 0) return FSB_OK;
+  row_map_kernel<<<(unsigned)fsb_ceil_div(n_rows, 256), 256, 0, s>>>(out_row_off, ncfg, row_cfg, n_rows);
+  FSB_LAUNCH_CHECK("row_map_kernel");
+  return FSB_OK;
+}
 
 size_t fsb_residual_ws_bytes(const fsb_context* h, int64_t n_rows, int k) {
   RowPlan pl = plan_rows(h, n_rows);

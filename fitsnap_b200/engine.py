@@ -323,6 +323,50 @@ class Engine:
             _ptr(A), A.stride(0) if A.shape[0] > 1 else lda, _ptr(b), _ptr(w), n_out, _ptr(batch.row_cfg), _ptr(nonfinite), self._stream()))
         return A, b, w, nonfinite
 
+    def row_map(self, out_row_off, ncfg, n_rows):
+        """int32 row -> configuration map of a batch (`fsb_row_map`)."""
+        m = torch.empty(int(n_rows), dtype=torch.int32, device=self.device)
+        _cabi.check("fsb_row_map", self.lib.fsb_row_map(self._h, _ptr(out_row_off), int(ncfg), _ptr(m), int(n_rows),
+                                                         self._stream()))
+        return m
+
+    def scatter_gram(self, batch, A=None, b=None, w=None, testing=None, lda=None, store_a=True):
+        """Fused K1 + K2..K4 (`fsb_scatter_gram`): assemble the rows of `batch` AND form their augmented Gram in one
+        pass over the raw blocks.  Returns (A, b, w, nonfinite, gaug) -- A is None with store_a=False (streaming mode)
+        -- or None when the layout is not covered by the fused kernel (the caller then runs scatter + gram)."""
+        if batch.row_cfg is None or batch.ncfg == 0 or batch.n_rows_out == 0:
+            return None
+        all_rows = _cabi.ROWS_ENERGY | _cabi.ROWS_FORCE | _cabi.ROWS_STRESS
+        k = batch.k
+        if (batch.flags & all_rows) != all_rows or (k + 1 + 7) // 8 > 13 or self.gram_path(batch.n_rows_out, k) != "fp64":
+            return None
+        lda = int(lda or k)
+        if b is None:
+            if store_a:
+                A = torch.empty((batch.row_end, lda), dtype=torch.float64, device=self.device)[:, :k]
+            b = torch.empty(batch.row_end, dtype=torch.float64, device=self.device)
+            w = torch.empty(batch.row_end, dtype=torch.float64, device=self.device)
+        if not store_a:
+            A = None
+        if testing is not None:
+            assert testing.dtype == torch.uint8 and testing.numel() == batch.n_rows_out and testing.is_contiguous()
+        n_out = batch.n_rows_out
+        gaug = torch.empty((k + 1, k + 1), dtype=torch.float64, device=self.device)
+        ws = self._workspace("gram", self.lib.fsb_gram_workspace_bytes(self._h, n_out, k))
+        nonfinite = torch.zeros(1, dtype=torch.int32, device=self.device)
+        a_lda = (A.stride(0) if A.shape[0] > 1 else lda) if A is not None else k
+        st = self.lib.fsb_scatter_gram(
+            self._h, _ptr(batch.raw), _ptr(batch.raw_row_off), _ptr(batch.out_row_off), _ptr(batch.natoms),
+            _ptr(batch.volume), _ptr(batch.energy), _ptr(batch.forces), _ptr(batch.stress),
+            _ptr(batch.eweight), _ptr(batch.fweight), _ptr(batch.vweight), _ptr(batch.type_fraction),
+            _ptr(batch.blank2j), batch.ncfg, batch.numtypes, batch.ncoeff, batch.flags,
+            _ptr(A), a_lda, _ptr(b), _ptr(w), n_out, _ptr(batch.row_cfg), _ptr(nonfinite), _ptr(testing), _ptr(gaug),
+            _ptr(ws), ws.numel(), self._stream())
+        if st == _cabi.UNSUPPORTED:
+            return None
+        _cabi.check("fsb_scatter_gram", st)
+        return A, b, w, nonfinite, gaug
+
     # ------------------------------------------------------------------ the fit
     def fit(self, A, b, w, testing=None, alpha=0.0, refine=2, group=None, diagnostics=True):
         return fit_rows(self, A, b, w, testing, alpha=alpha, refine=refine, group=group, diagnostics=diagnostics)

@@ -26,6 +26,9 @@ class LinearFitPipeline:
         self.alpha, self.refine, self.group = float(alpha), refine, group
         self.scrub = bool(scrub_nonfinite)
 
+    #: narrow layouts (k + 1 <= 104, E + F + S rows, row map given) go through the fused scatter + Gram kernel
+    fuse_scatter_gram = True
+
     def pack(self, blocks, natoms, volumes, energies, forces, stresses, eweights, fweights, vweights,
              type_fraction=None, first_row=0) -> ConfigBatch:
         e, f, s = self.rows
@@ -35,9 +38,16 @@ class LinearFitPipeline:
 
     def fit_batch(self, batch: ConfigBatch, testing=None, out=None) -> FitResult:
         """Device-resident step: scatter -> Gram -> (all-reduce) -> factor/solve -> refinement."""
-        A, b, w, bad = self.engine.scatter(batch, *(out or (None, None, None)))
-        res = self.engine.fit(A, b, w, testing, alpha=self.alpha, refine=self.refine, group=self.group,
-                              diagnostics=False)
+        fused = self.engine.scatter_gram(batch, *(out or (None, None, None)), testing=testing) \
+            if (self.fuse_scatter_gram and hasattr(self.engine, "scatter_gram")) else None
+        if fused is not None:       # rows assembled and contracted in one pass (fsb_scatter_gram)
+            A, b, w, bad, gaug = fused
+            res = fit_rows(self.engine, A, b, w, testing, alpha=self.alpha, refine=self.refine, group=self.group,
+                           diagnostics=False, gaug=gaug)
+        else:
+            A, b, w, bad = self.engine.scatter(batch, *(out or (None, None, None)))
+            res = self.engine.fit(A, b, w, testing, alpha=self.alpha, refine=self.refine, group=self.group,
+                                  diagnostics=False)
         res.extra.update(A=A, b=b, w=w, nonfinite=bad)
         return res
 
@@ -139,9 +149,14 @@ class LinearFitPipeline:
             main.wait_event(ev)
             batches.append(batch)
             h2d += batch.h2d_bytes
-            _, _, _, bad_c = eng.scatter(batch, A, b, w, lda=k)
             r0, r1 = int(out_off[c0]), int(out_off[c1])
-            g_c = eng.gram(A[r0:r1], b[r0:r1], w[r0:r1], None if T is None else T[r0:r1])
+            fused = eng.scatter_gram(batch, A, b, w, testing=None if T is None else T[r0:r1], lda=k) \
+                if self.fuse_scatter_gram else None
+            if fused is not None:
+                bad_c, g_c = fused[3], fused[4]
+            else:
+                _, _, _, bad_c = eng.scatter(batch, A, b, w, lda=k)
+                g_c = eng.gram(A[r0:r1], b[r0:r1], w[r0:r1], None if T is None else T[r0:r1])
             gaug = g_c if gaug is None else gaug.add_(g_c)
             bad = bad_c if bad is None else bad.add_(bad_c)
         res = fit_rows(eng, A, b, w, T, alpha=self.alpha, refine=self.refine, group=self.group, diagnostics=False,

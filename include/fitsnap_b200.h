@@ -108,6 +108,29 @@ int fsb_scatter(fsb_handle_t h, const double* raw, const int64_t* raw_row_off,
                 double* b, double* w, int64_t n_rows_out, const int32_t* row_cfg, int32_t* nonfinite,
                 void* stream);
 
+/* row -> configuration map of a batch (the `row_cfg` argument of fsb_scatter / fsb_scatter_gram, which selects
+ * their TMA-staged fast paths): row_cfg[i] = configuration that owns output row out_row_off[0] + i. */
+int fsb_row_map(fsb_handle_t h, const int64_t* out_row_off, int32_t ncfg, int32_t* row_cfg, int64_t n_rows_out,
+                void* stream);
+
+/* ---- K1 + K2..K4 fused: row build + scatter + Gram in ONE pass over the raw blocks --------------------------
+ * The per-batch accumulation of examples/library/transpose_trick/example.py:226-246
+ *     a, b, w = calculator.process_single(configuration, i);  aw, bw = w[:, None] * a, w * b
+ *     c += aw.T @ aw;  d += aw.T @ bw
+ * for a whole batch of configurations: arguments of fsb_scatter + the test mask, output of fsb_gram.  The rows are
+ * weighted and contracted straight from the registers that assemble them -- the design matrix is not read back.
+ * A may be NULL (streaming mode: A is never materialised; b and w always are).  Results are bit-identical to
+ * fsb_scatter followed by fsb_gram.  Covers the common layout only -- all three row families (FSB_ROWS_ENERGY |
+ * FORCE | STRESS), row_cfg given, k + 1 <= 104, fp64 Gram path -- and returns FSB_ERR_UNSUPPORTED otherwise (call
+ * fsb_scatter + fsb_gram then).  Workspace: fsb_gram_workspace_bytes(h, n_rows_out, k). */
+int fsb_scatter_gram(fsb_handle_t h, const double* raw, const int64_t* raw_row_off, const int64_t* out_row_off,
+                     const int32_t* natoms, const double* volume, const double* energy, const double* forces,
+                     const double* stress, const double* eweight, const double* fweight, const double* vweight,
+                     const double* type_fraction, const double* blank2j, int32_t ncfg, int32_t numtypes,
+                     int32_t ncoeff, int32_t flags, double* A, int64_t lda, double* b, double* w, int64_t n_rows_out,
+                     const int32_t* row_cfg, int32_t* nonfinite, const uint8_t* testing, double* gaug, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* ---- K2+K3+K4: fused mask + row weighting + Gram ------------------------------------
  * Replaces the prologue and contraction of SVD/RIDGE/LASSO.perform_fit
  * (solvers/svd.py:35-53, solvers/ridge.py:28-43, solvers/lasso.py:19-24) and the

@@ -1,0 +1,116 @@
+"""GPU parity of the fused scatter + Gram kernel (`fsb_scatter_gram`, csrc/gram_small.cu: scatter_gram_kernel):
+rows bit-exact against the oracle's restatement of `_collect_lammps` (lammps_snap.py:391-556), augmented Gram
+BIT-IDENTICAL to the two-kernel path (fsb_scatter -> fsb_gram) on the same batch -- with and without a test mask, with
+row offsets, with A not materialised (streaming mode of examples/library/transpose_trick/example.py:226-246)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import linear_fit as lf
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(engine, rng, ncfg, nt, nc, bz, first_row=0, max_atoms=17, scrub=False):
+    from fitsnap_b200.assembly import pack_configs
+    kraw = nt * nc
+    k = kraw + (0 if bz else nt)
+    natoms = rng.integers(1, max_atoms, ncfg).astype(np.int32)
+    blocks = [rng.standard_normal((7 + 3 * n, kraw + 1)) * 10.0 ** rng.uniform(-2, 2, (1, kraw + 1)) for n in natoms]
+    vol = rng.uniform(50, 500, ncfg)
+    energy = rng.normal(-5, 1, ncfg) * natoms
+    forces = [rng.standard_normal((n, 3)) for n in natoms]
+    stress = rng.standard_normal((ncfg, 3, 3)) * 1e3
+    stress = 0.5 * (stress + stress.transpose(0, 2, 1))
+    ew, fw, vw = 10.0 ** rng.uniform(-1, 2, ncfg), 10.0 ** rng.uniform(-1, 1, ncfg), 10.0 ** rng.uniform(-6, -4, ncfg)
+    tf = rng.dirichlet(np.ones(nt), ncfg)
+    b2j = np.ones(k)
+    b2j[rng.choice(k, min(3, k - 1), replace=False)] = 0.0
+    cfgs = [dict(block=blocks[c], natoms=int(natoms[c]), volume=vol[c], energy=energy[c], forces=forces[c],
+                 stress=stress[c], eweight=ew[c], fweight=fw[c], vweight=vw[c], type_fraction=tf[c])
+            for c in range(ncfg)]
+    batch = pack_configs(engine, np.concatenate(blocks), natoms, vol, energy, np.concatenate(forces), stress, ew, fw,
+                         vw, tf, b2j, nt, nc, bzeroflag=bz, first_row=first_row, scrub_nonfinite=scrub)
+    return batch, cfgs, b2j, k
+
+
+@pytest.mark.parametrize("ncfg,nt,nc,bz,first_row", [(3, 1, 5, 1, 0), (40, 2, 14, 0, 0), (900, 2, 49, 0, 0),
+                                                     (900, 2, 51, 1, 5), (700, 3, 30, 0, 11), (1500, 1, 30, 0, 0)])
+def test_fused_scatter_gram_equals_two_kernel_path(engine, ncfg, nt, nc, bz, first_row):
+    rng = np.random.default_rng(ncfg + 7 * nc + bz)
+    batch, cfgs, b2j, k = _batch(engine, rng, ncfg, nt, nc, bz, first_row)
+    a, b, w = lf.assemble(cfgs, nt, nc, bz, b2j)
+    n = a.shape[0]
+    dev = engine.device
+    new = lambda *shape: torch.full(shape, -7.0, dtype=torch.float64, device=dev)
+    A1, B1, W1 = new(first_row + n, k), new(first_row + n), new(first_row + n)
+    engine.scatter(batch, A1, B1, W1, lda=k)
+    t_host = rng.random(n) < 0.2
+    T = engine.to_device(t_host.astype(np.uint8), dtype=torch.uint8)
+    for testing in (None, T):
+        g_ref = engine.gram(A1[first_row:], B1[first_row:], W1[first_row:], testing).clone()
+        A2, B2, W2 = new(first_row + n, k), new(first_row + n), new(first_row + n)
+        out = engine.scatter_gram(batch, A2, B2, W2, testing=testing, lda=k)
+        assert out is not None, "fused kernel refused a layout it should cover"
+        _, _, _, bad, g = out
+        assert int(bad.item()) == 0
+        assert np.array_equal(A2[first_row:].cpu().numpy(), a) and np.array_equal(B2[first_row:].cpu().numpy(), b)
+        assert np.array_equal(W2[first_row:].cpu().numpy(), w)
+        assert bool((A2[:first_row] == -7.0).all()) and bool((B2[:first_row] == -7.0).all())
+        assert torch.equal(g, g_ref), float((g - g_ref).abs().max())
+    # streaming mode: A is not materialised, the Gram is the same
+    B3, W3 = new(first_row + n), new(first_row + n)
+    out = engine.scatter_gram(batch, None, B3, W3, testing=T, store_a=False)
+    assert out[0] is None and torch.equal(out[4], g_ref)
+    assert np.array_equal(B3[first_row:].cpu().numpy(), b) and np.array_equal(W3[first_row:].cpu().numpy(), w)
+
+
+def test_fused_scatter_gram_on_reference_fixtures(engine):
+    """The reference-generated scatter fixtures with all three row families (SNAP b0/b1, PACE b0/b1 with scrubbing)."""
+    from fitsnap_b200.assembly import pack_configs
+    for tag in ("snap_b0_efs", "snap_b1_efs", "pace_b0_efs", "pace_b1_efs"):
+        g = load_golden("scatter_%s.npz" % tag)
+        batch = pack_configs(engine, g["raw"], g["natoms"], g["volume"], g["energy"], g["forces"], g["stress"], g["eweight"],
+                             g["fweight"], g["vweight"], g["type_fraction"], g["blank2j"], int(g["numtypes"]),
+                             int(g["ncoeff"]), bzeroflag=bool(g["bzeroflag"]), scrub_nonfinite=tag.startswith("pace"))
+        T = engine.to_device(g["ref_testing"].astype(np.uint8), dtype=torch.uint8)
+        A, b, w, bad, gaug = engine.scatter_gram(batch, testing=T)
+        assert np.array_equal(A.cpu().numpy(), g["ref_a"]) and np.array_equal(b.cpu().numpy(), g["ref_b"])
+        assert np.array_equal(w.cpu().numpy(), g["ref_w"]) and int(bad.item()) == 0
+        assert torch.equal(gaug, engine.gram(A, b, w, T))
+
+
+def test_fused_scatter_gram_nonfinite_and_unsupported_layouts(engine):
+    from fitsnap_b200.assembly import pack_configs
+    rng = np.random.default_rng(3)
+    batch, cfgs, b2j, k = _batch(engine, rng, 300, 2, 14, 0)
+    raw = batch.raw.clone()
+    raw[1234, 5] = float("nan")
+    batch.raw = raw
+    out = engine.scatter_gram(batch)
+    assert int(out[3].item()) > 0                       # counted, like fsb_scatter (lammps_snap.py:426-428 raises from it)
+    # wide matrices and layouts without all three row families are not covered: the caller gets None
+    wide, *_ = _batch(engine, rng, 20, 2, 70, 0)
+    assert engine.scatter_gram(wide) is None
+    g = load_golden("scatter_snap_b0_ef.npz")
+    ef = pack_configs(engine, g["raw"], g["natoms"], g["volume"], g["energy"], g["forces"], g["stress"], g["eweight"],
+                      g["fweight"], g["vweight"], g["type_fraction"], g["blank2j"], int(g["numtypes"]), int(g["ncoeff"]),
+                      stress=False, bzeroflag=False)
+    assert engine.scatter_gram(ef) is None
+
+
+def test_pipeline_uses_the_fused_kernel_and_matches_the_unfused_fit(engine):
+    from fitsnap_b200.pipeline import LinearFitPipeline
+    rng = np.random.default_rng(9)
+    batch, cfgs, b2j, k = _batch(engine, rng, 800, 2, 20, 0)
+    pipe = LinearFitPipeline(2, 20, False, b2j, alpha=1e-8, refine=2, engine=engine)
+    n0 = engine.launch_count
+    fused = pipe.fit_batch(batch)
+    n_fused = engine.launch_count - n0
+    pipe.fuse_scatter_gram = False
+    n0 = engine.launch_count
+    plain = pipe.fit_batch(batch)
+    n_plain = engine.launch_count - n0
+    assert torch.equal(fused.x, plain.x) and torch.equal(fused.gaug, plain.gaug)
+    assert n_fused == n_plain - 1                      # one kernel fewer: scatter + Gram in one launch
