@@ -360,7 +360,8 @@ static size_t partial_bytes(const GramPlan& pl) {
 // fused K1 + K2..K4 for narrow matrices (gram_small.cu: scatter_gram_kernel) + the deterministic split-K reduction
 bool fsb_scatter_gram_supported(const ScatterArgs& sc, int64_t total);
 int fsb_launch_scatter_gram_small(const fsb_context* h, const ScatterArgs& sc, const uint8_t* testing, int64_t total,
-                                  int store_a, double* partial, cudaStream_t s);
+                                  int store_a, double* partial, void* desc, cudaStream_t s);
+size_t fsb_scatter_gram_desc_bytes(int64_t total);
 
 int fsb_launch_scatter_gram(const fsb_context* h, const ScatterArgs& sc, const uint8_t* testing, int64_t total,
                             int store_a, double* gaug, void* ws, size_t ws_bytes, cudaStream_t s) {
@@ -369,8 +370,10 @@ int fsb_launch_scatter_gram(const fsb_context* h, const ScatterArgs& sc, const u
   const int k = sc.ncoeff * sc.numtypes + (bzero ? 0 : sc.numtypes);
   if (fsb_gram_path_for(h, total, k) != FSB_GRAM_FP64 || !use_small(k)) return FSB_ERR_UNSUPPORTED;
   GramPlan pl = effective_plan(h, total, k);
-  if (ws_bytes < align256(partial_bytes(pl))) return FSB_ERR_WORKSPACE_TOO_SMALL;
-  int st = fsb_launch_scatter_gram_small(h, sc, testing, total, store_a, (double*)ws, s);
+  // the per-row descriptors live where the unfused path keeps its masked weights / pre-weighted copy
+  const size_t off_desc = align256(partial_bytes(pl));
+  if (ws_bytes < off_desc + fsb_scatter_gram_desc_bytes(total)) return FSB_ERR_WORKSPACE_TOO_SMALL;
+  int st = fsb_launch_scatter_gram_small(h, sc, testing, total, store_a, (double*)ws, (char*)ws + off_desc, s);
   if (st != FSB_OK) return st;
   const int ka = k + 1;
   dim3 rgrid((unsigned)fsb_ceil_div(ka, 32), (unsigned)ka);
@@ -383,9 +386,11 @@ size_t fsb_gram_ws_bytes(const fsb_context* h, int64_t n_rows, int k) {
   if (fsb_gram_path_for(h, n_rows, k) == FSB_GRAM_INT8)
     return align256((size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double)) + fsb_gram_i8_ws_bytes(n_rows, k);
   GramPlan pl = effective_plan(h, n_rows, k);
-  // split-K partials + masked weight vector (test mask given) + pre-weighted copy (wide matrices)
-  return align256(partial_bytes(pl)) + align256((size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double)) +
-         waug_bytes(n_rows, k);
+  // split-K partials + masked weight vector (test mask given) + pre-weighted copy (wide matrices); narrow matrices:
+  // room for the 24-byte row descriptors of the fused scatter + Gram kernel instead
+  const size_t tail = align256((size_t)(n_rows > 0 ? n_rows : 1) * sizeof(double)) + waug_bytes(n_rows, k);
+  const size_t desc = use_small(k) ? align256(fsb_scatter_gram_desc_bytes(n_rows)) : 0;
+  return align256(partial_bytes(pl)) + (tail > desc ? tail : desc);
 }
 
 int fsb_launch_gram(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* w,

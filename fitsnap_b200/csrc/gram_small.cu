@@ -74,9 +74,15 @@ __device__ __forceinline__ void bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+// `wring` == nullptr: the ring holds weighted rows (gram_rowsplit_kernel: the producers multiplied).  Otherwise the
+// ring holds UNWEIGHTED rows and wring[slot][row] their weights: the consumer scales its fragments, fl(w * a) exactly
+// as a producer would (svd.py:44), right before the DMMAs that use them.  The fp64 pipe is shared by DMUL and DMMA: a
+// producer warp's DMUL queues behind the consumers' DMMAs (~130 cycles each, measured: the producers of the fused
+// kernel spent most of a stage waiting for 32 multiplies), whereas 13 DMULs in front of 21-25 DMMAs of the same
+// warp cost ~7 % of the pipe.
 template <int R0, int R1>
 __device__ __forceinline__ void consume(double* partial, const double* smem, int pitch, int nstage, int group,
-                                        int lane, int nsteps, int64_t cta) {
+                                        int lane, int nsteps, int64_t cta, const double* wring = nullptr) {
   constexpr int NACC = (R1 * (R1 + 1) - R0 * (R0 + 1)) / 2 > 0 ? (R1 * (R1 + 1) - R0 * (R0 + 1)) / 2 : 1;
   constexpr int base = R0 * (R0 + 1) / 2;
   double acc[NACC][2];
@@ -100,6 +106,11 @@ __device__ __forceinline__ void consume(double* partial, const double* smem, int
         const double* frow = st + (group + S_GROUPS * (q + 1)) * 4 * pitch;   // this group's next k-step
 #pragma unroll
         for (int c = 0; c < R1; ++c) f[(q + 1) & 1][c] = frow[c * 8];
+      }
+      if (wring) {
+        const double wq = wring[slot * S_RCH + (group + S_GROUPS * q) * 4 + (lane & 3)];
+#pragma unroll
+        for (int c = 0; c < R1; ++c) f[q & 1][c] *= wq;
       }
 #pragma unroll
       for (int i = R0; i < R1; ++i)
@@ -283,43 +294,137 @@ struct FusedArgs {
   int64_t total;            // rows of this call
   int64_t rows_per_cta;
   double* partial;
+  const struct FusedDesc* desc;   // per-row descriptors (row_resolve_kernel)
   int store_a;              // 0: streaming mode, A is not materialised (b and w still are)
 };
 
-struct FusedM2 {            // second level of the metadata chain (lane = row)
-  int cfg, nat;
-  unsigned tst;
-  int64_t off;
-  double ew, fw, vw, en, vol, fo;
-};
-struct FusedRow {           // resolved row (lane = row)
-  double div, wv, truth, wg;   // wg: weight seen by the Gram (0 for test rows and rows past the end)
-  int kind, cfg;               // kind: 0 energy, 1 force, 2 virial, -1 past the end
+struct FusedDesc {           // one per output row, written by row_resolve_kernel
+  double wg;                 // weight seen by the Gram: w, or 0 for a test row
+  double div;                // N (energy row), V (virial row), 1 (force row)
+  int kind;                  // 0 energy, 1 force, 2 virial
+  int cfg;
 };
 
+// Row metadata is a chain of dependent global loads (row -> configuration -> offsets / weights / truth -> stress
+// component): resolved here for every row at once -- b and w are final after this kernel, the fused kernel below reads
+// one 24-byte descriptor per row.  ~1e6 rows: tens of microseconds, 2 % of the fused kernel's traffic.
+__global__ void __launch_bounds__(256) row_resolve_kernel(ScatterArgs a, const uint8_t* __restrict__ testing, int64_t total,
+                                                          FusedDesc* __restrict__ desc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const bool do_scrub = a.flags & FSB_SCRUB_NONFINITE;
+  const int kraw = a.ncoeff * a.numtypes;
+  const int64_t ldr = kraw + 1;
+  const int64_t row0 = __ldg(a.out_row_off), rraw0 = __ldg(a.raw_row_off);
+  const int64_t n_force = total - 7 * (int64_t)a.ncfg > 1 ? total - 7 * (int64_t)a.ncfg : 1;   // 3 * atoms
+  const int c = __ldg(a.row_cfg + i);
+  double ref = __ldg(a.raw + (rraw0 + i) * ldr + kraw);       // reference-potential column of this row
+  int64_t fi = i - 7 * (int64_t)c - 1;                        // rows map 1:1 (see scatter_bulk_kernel)
+  fi = fi < 0 ? 0 : (fi > n_force - 1 ? n_force - 1 : fi);
+  const int nat = __ldg(a.natoms + c);
+  const int64_t off_c = __ldg(a.out_row_off + c);
+  const double ew = __ldg(a.eweight + c), fw = __ldg(a.fweight + c), vw = __ldg(a.vweight + c);
+  const double en = __ldg(a.energy + c), vol = __ldg(a.volume + c), fo = __ldg(a.forces + fi);
+  const int64_t local = row0 + i - off_c;
+  FusedDesc d;
+  double truth, wv;
+  d.cfg = c;
+  if (local == 0) {
+    d.kind = 0; d.div = (double)nat; wv = ew; truth = en;
+  } else if (local < 1 + 3 * (int64_t)nat) {
+    d.kind = 1; d.div = 1.0; wv = fw; truth = fo;
+  } else {
+    const int sub = (int)(local - 1 - 3 * (int64_t)nat);
+    const int vi[6] = {0, 1, 2, 1, 0, 0}, vj[6] = {0, 1, 2, 2, 2, 1};
+    d.kind = 2; d.div = vol; wv = vw;
+    truth = __ldg(a.stress + (size_t)c * 9 + vi[sub] * 3 + vj[sub]);
+  }
+  bool bad = false;
+  ref = fsb_dev::scrub(ref, do_scrub, bad);
+  if (bad && a.nonfinite) atomicAdd(a.nonfinite, 1);
+  a.b[row0 + i] = (d.kind == 0) ? (truth - ref) / d.div : truth - ref;     // lammps_snap.py:473, :506-507, :540-541
+  a.w[row0 + i] = wv;
+  d.wg = (testing && __ldg(testing + i)) ? 0.0 : wv;
+  desc[i] = d;
+}
+
+// value of A for an energy / virial row (or any row when non-finite raw values are being scrubbed): out of line, the two
+// fp64 divisions exist once in the kernel
+__device__ __noinline__ double fused_special_row(double x, int kind, double div, double tf, double pref, bool loads_raw,
+                                                 bool do_scrub) {
+  bool dummy = false;
+  if (do_scrub) x = fsb_dev::scrub(x, true, dummy);
+  if (kind == 1) return (loads_raw ? x : 0.0) * pref;                                   // lammps_snap.py:493-502
+  if (kind == 2) return (loads_raw ? (FSB_VIRIAL_UNIT * x) / div : 0.0) * pref;         // :526-536
+  return (loads_raw ? x / div : tf) * pref;                                             // :435-467
+}
+
+__device__ __forceinline__ unsigned fz_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fz_mbar_wait(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  for (unsigned spin = 0; spin < (1u << 26); ++spin) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();      // protocol error: fail the launch instead of hanging the device
+}
+
+__device__ __forceinline__ double fz_lds(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void fz_sts(unsigned addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+constexpr int FZ_RAW_STAGES = 3;     // raw tiles in flight per SM (TMA bulk copies)
+constexpr int FZ_PBAR = 15;          // named barrier of the 128 producer threads
+
 template <int NB>
-__global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p) {
-  extern __shared__ double smem[];   // [NSTAGE][S_RCH x PITCH]
+__global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p, int nstage_d) {
+  extern __shared__ __align__(128) double smem[];   // [nstage_d][S_RCH x PITCH] DMMA ring | [FZ_RAW_STAGES][S_RCH x ldr] raw ring
+  __shared__ __align__(8) unsigned long long raw_full[FZ_RAW_STAGES];
+  __shared__ __align__(8) unsigned long long raw_empty[FZ_RAW_STAGES];
+  __shared__ __align__(16) double wring[S_MAXSTAGE * S_RCH];          // Gram weights of the rows of every ring stage
   constexpr int PITCH = 8 * NB + 4;
-  constexpr int NSTAGE = ring_depth(NB);
   constexpr int KP = 8 * NB;
-  constexpr int HALF = S_RCH / 2;
   const ScatterArgs& a = p.sc;
   const bool bzero = a.flags & FSB_BZEROFLAG, do_scrub = a.flags & FSB_SCRUB_NONFINITE;
   const int kraw = a.ncoeff * a.numtypes;
   const int k = bzero ? kraw : kraw + a.numtypes;
   const int seg = a.ncoeff + 1;
-  const int64_t ldr = kraw + 1;
+  const int ldr = kraw + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t cta = blockIdx.x;
   const int64_t row_begin = cta * p.rows_per_cta;
   int64_t row_end = row_begin + p.rows_per_cta;
   if (row_end > p.total) row_end = p.total;
   const int nsteps = row_end > row_begin ? (int)((row_end - row_begin + S_RCH - 1) / S_RCH) : 0;
+  double* raw_ring = smem + (size_t)nstage_d * (S_RCH * PITCH);
+  const int raw_stage = S_RCH * ldr;                       // doubles per raw tile
+
+  if (tid == S_CONSUMERS) {
+    for (int i = 0; i < FZ_RAW_STAGES; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fz_smem_u32(&raw_full[i])), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fz_smem_u32(&raw_empty[i])), "r"(S_PRODUCERS / 32)
+                   : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
   if (warp >= S_CONSUMERS / 32) {
-    const int c = tid - S_CONSUMERS;          // column of the augmented matrix owned by this thread
-    int srcc = INT_MIN;                       // >= 0: raw column; < 0: lead column of type (-v-1); INT_MIN: padding
+    const int c = tid - S_CONSUMERS;          // column of A owned by this thread (the b column belongs to warp 0's lanes)
+    int srcc = INT_MIN;                       // >= 0: raw column; < 0: lead column of type (-v-1); INT_MIN: not a column of A
     double pref = 0.0;
     if (c < k) {
       int v = c;
@@ -329,129 +434,158 @@ __global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p)
       }
       srcc = v;
       pref = __ldg(a.blank2j + c);
-    } else if (c == k) {
-      srcc = kraw;                            // reference-potential column
     }
+    const bool unit_pref = pref == 1.0;       // blank2J is a 0/1 mask in practice: x * 1.0 == x, and the fp64 pipe
+                                              // (shared with the consumers' DMMAs) is spared one multiply per element
     const int64_t row0 = a.out_row_off[0], rraw0 = a.raw_row_off[0];
-    const int64_t n_force = p.total - 7 * (int64_t)a.ncfg > 1 ? p.total - 7 * (int64_t)a.ncfg : 1;   // 3 * atoms
-    const double* rawc = a.raw + rraw0 * ldr + (srcc >= 0 ? srcc : 0);
+    const double* raw0 = a.raw + rraw0 * (int64_t)ldr;          // raw row of output row index 0 of this call
     const bool loads_raw = srcc >= 0;
+    const bool acol = c < k, do_store = acol && p.store_a;
+    const bool bwarp = warp == S_CONSUMERS / 32;
+    const bool ring_thread = c < KP && c != k;
+    const bool warp_unit_pref = __all_sync(0xffffffffu, unit_pref || !acol);     // warp-uniform
     bool bad = false;
 
-    auto level1 = [&](int s, int& cfg, unsigned& tst) {
+    // The TMA unit moves the raw tiles (one elected thread, cp.async.bulk + mbarrier complete_tx, FZ_RAW_STAGES tiles in
+    // flight): a producer thread holds no load registers and computes no global load addresses.  A stage (32 rows) is
+    // transformed from shared memory in two passes:
+    //   pass 1, one basic block: every row is treated as a force row (93 % of them are: A = R * blank2J);
+    //   pass 2, warp-uniform bit tests: energy / virial rows (divisions, type fractions; ~7 % of the rows) are redone
+    //           by an out-of-line routine and overwrite what pass 1 stored.
+    // Lane r of every producer warp holds the descriptor of row r of the stage (loaded one stage ahead); the b column
+    // of the ring is written by lane r of producer warp 0.
+    auto tile_is_bulk = [&](int t) {
+      const int64_t i0 = row_begin + (int64_t)t * S_RCH;
+      return (row_end - i0) >= S_RCH && (reinterpret_cast<uintptr_t>(raw0 + i0 * ldr) & 15) == 0;
+    };
+    auto issue_tile = [&](int t) {            // elected thread only
+      if (t >= nsteps) return;
+      const int slot = t % FZ_RAW_STAGES, n = t / FZ_RAW_STAGES;
+      if (t >= FZ_RAW_STAGES) fz_mbar_wait(fz_smem_u32(&raw_empty[slot]), (unsigned)((n - 1) & 1));
+      const unsigned full = fz_smem_u32(&raw_full[slot]);
+      if (tile_is_bulk(t)) {
+        const unsigned bytes = (unsigned)(raw_stage * sizeof(double));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(fz_smem_u32(raw_ring + (size_t)slot * raw_stage)),
+                       "l"(raw0 + (row_begin + (int64_t)t * S_RCH) * ldr), "r"(bytes), "r"(full) : "memory");
+      } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");   // filled by the producers
+      }
+    };
+    struct StageDesc { double wg, div, bval; int kind, cfg; };
+    auto load_desc = [&](int s, StageDesc& d) {
+      d.wg = 0.0; d.div = 1.0; d.bval = 0.0; d.kind = -1; d.cfg = 0;
       const int64_t i = row_begin + (int64_t)s * S_RCH + lane;
-      cfg = -1;
-      tst = 0u;
       if (s < nsteps && i < row_end) {
-        cfg = __ldg(a.row_cfg + i);
-        if (p.testing) tst = (unsigned)__ldg(p.testing + i);
-      }
-    };
-    auto level2 = [&](int s, int cfg, unsigned tst, FusedM2& m) {
-      m.cfg = cfg; m.tst = tst; m.nat = 1; m.off = 0;
-      m.ew = m.fw = m.vw = m.en = m.vol = m.fo = 0.0;
-      if (cfg >= 0) {
-        const int64_t i = row_begin + (int64_t)s * S_RCH + lane;
-        int64_t fi = i - 7 * (int64_t)cfg - 1;                 // rows map 1:1 (see scatter_bulk_kernel)
-        fi = fi < 0 ? 0 : (fi > n_force - 1 ? n_force - 1 : fi);
-        m.nat = __ldg(a.natoms + cfg);
-        m.off = __ldg(a.out_row_off + cfg);
-        m.ew = __ldg(a.eweight + cfg); m.fw = __ldg(a.fweight + cfg); m.vw = __ldg(a.vweight + cfg);
-        m.en = __ldg(a.energy + cfg); m.vol = __ldg(a.volume + cfg); m.fo = __ldg(a.forces + fi);
-      }
-    };
-    auto level3 = [&](int s, const FusedM2& m, FusedRow& r) {
-      r.kind = -1; r.cfg = 0; r.div = 1.0; r.wv = 0.0; r.truth = 0.0; r.wg = 0.0;
-      if (m.cfg >= 0) {
-        const int64_t i = row_begin + (int64_t)s * S_RCH + lane;
-        const int64_t local = row0 + i - m.off;
-        r.cfg = m.cfg;
-        if (local == 0) {
-          r.kind = 0; r.div = (double)m.nat; r.wv = m.ew; r.truth = m.en;
-          if (!bzero) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.type_fraction + (size_t)m.cfg * a.numtypes));
-        } else if (local < 1 + 3 * (int64_t)m.nat) {
-          r.kind = 1; r.wv = m.fw; r.truth = m.fo;
-        } else {
-          const int sub = (int)(local - 1 - 3 * (int64_t)m.nat);
-          const int vi[6] = {0, 1, 2, 1, 0, 0}, vj[6] = {0, 1, 2, 2, 2, 1};
-          r.kind = 2; r.div = m.vol; r.wv = m.vw;
-          r.truth = __ldg(a.stress + (size_t)m.cfg * 9 + vi[sub] * 3 + vj[sub]);
-        }
-        r.wg = m.tst ? 0.0 : r.wv;
-      }
-    };
-    auto load_half = [&](int h, double (&v)[HALF]) {
-      const int64_t i0 = row_begin + (int64_t)h * HALF;
-#pragma unroll
-      for (int j = 0; j < HALF; ++j) {
-        const int64_t i = i0 + j;
-        const int64_t ic = i < row_end ? i : row_end - 1;        // clamped; rows past the end are not used
-        v[j] = loads_raw ? __ldg(rawc + ic * ldr) : 0.0;
-      }
-    };
-    auto store_half = [&](int h, const double (&v)[HALF], const FusedRow& r) {
-      const int s = h >> 1;
-      const int slot = s % NSTAGE;
-      double* st = smem + (size_t)slot * (S_RCH * PITCH) + c;
-      const int64_t i0 = row_begin + (int64_t)h * HALF;
-#pragma unroll
-      for (int j = 0; j < HALF; ++j) {
-        const int rr = (h & 1) * HALF + j;
-        const int kind = __shfl_sync(0xffffffffu, r.kind, rr);
-        const double div = __shfl_sync(0xffffffffu, r.div, rr);
-        const double wg = __shfl_sync(0xffffffffu, r.wg, rr);
-        const double wv = __shfl_sync(0xffffffffu, r.wv, rr);
-        const double truth = __shfl_sync(0xffffffffu, r.truth, rr);
-        const int cfg = __shfl_sync(0xffffffffu, r.cfg, rr);
-        double out = 0.0;
-        if (kind >= 0 && c <= k) {
-          const int64_t orow = row0 + i0 + j;
-          double x = v[j];
-          if (loads_raw && (((unsigned)__double2hiint(x) & 0x7ff00000u) == 0x7ff00000u)) x = fsb_dev::scrub(x, do_scrub, bad);
-          if (c < k) {
-            double val;
-            if (kind == 1) val = (loads_raw ? x : 0.0) * pref;                                  // lammps_snap.py:493-502
-            else if (kind == 2) val = (loads_raw ? (FSB_VIRIAL_UNIT * x) / div : 0.0) * pref;   // :526-536
-            else val = (loads_raw ? x / div
-                                  : __ldg(a.type_fraction + (size_t)cfg * a.numtypes + (-srcc - 1))) * pref;   // :435-467
-            if (p.store_a) a.A[orow * a.lda + c] = val;
-            out = val * wg;                                                                     // fl(w*a) (svd.py:44)
-          } else {
-            const double bv = (kind == 0) ? (truth - x) / div : truth - x;                      // :473, :506-507, :540-541
-            a.b[orow] = bv;
-            a.w[orow] = wv;
-            out = bv * wg;
-          }
-        }
-        if (c < KP) st[rr * PITCH] = out;
+        const FusedDesc* g = p.desc + i;
+        d.wg = __ldg(&g->wg); d.div = __ldg(&g->div); d.kind = __ldg(&g->kind); d.cfg = __ldg(&g->cfg);
+        if (bwarp) d.bval = __ldg(a.b + row0 + i);
       }
     };
 
-    // metadata pipeline: cfg of stage s+3, level 2 of stage s+2, level 3 of stage s+1 are issued while stage s is stored
-    int cfg1 = -1, cfg2 = -1, cfgN = -1;
-    unsigned tst1 = 0u, tst2 = 0u, tstN = 0u;
-    FusedM2 m2a, m2b;
-    FusedRow rowA, rowB;
-    level1(0, cfg1, tst1);
-    level2(0, cfg1, tst1, m2a);
-    level3(0, m2a, rowA);                 // stage 0 ready
-    level1(1, cfg1, tst1);
-    level2(1, cfg1, tst1, m2a);           // stage 1: level 2 in flight
-    level1(2, cfg2, tst2);                // stage 2: level 1 in flight
-    double va[HALF], vb[HALF];
-    if (nsteps > 0) load_half(0, va);
+    if (c == 0)
+      for (int t = 0; t < FZ_RAW_STAGES - 1; ++t) issue_tile(t);
+    StageDesc dA, dB;
+    load_desc(0, dA);
     for (int s = 0; s < nsteps; ++s) {
-      level1(s + 3, cfgN, tstN);
-      level2(s + 2, cfg2, tst2, m2b);
-      level3(s + 1, m2a, rowB);
-      load_half(2 * s + 1, vb);
-      if (s >= NSTAGE) bar_sync(1 + S_MAXSTAGE + (s % NSTAGE), S_THREADS);   // EMPTY[slot]
-      store_half(2 * s, va, rowA);
-      if (s + 1 < nsteps) load_half(2 * s + 2, va);
-      store_half(2 * s + 1, vb, rowA);
+      if (c == 0) issue_tile(s + FZ_RAW_STAGES - 1);
+      load_desc(s + 1, dB);
+      const unsigned valid = __ballot_sync(0xffffffffu, dA.kind >= 0);
+      const unsigned special = __ballot_sync(0xffffffffu, dA.kind == 0 || dA.kind == 2);
+      const int rslot = s % FZ_RAW_STAGES;
+      double* rtile = raw_ring + (size_t)rslot * raw_stage;
+      fz_mbar_wait(fz_smem_u32(&raw_full[rslot]), (unsigned)((s / FZ_RAW_STAGES) & 1));
+      if (!tile_is_bulk(s)) {                 // ragged last tile / misaligned view: plain loads, all producers
+        const int64_t i0 = row_begin + (int64_t)s * S_RCH;
+        const int nr = (int)((row_end - i0) < S_RCH ? (row_end - i0) : S_RCH);
+        const double* src = raw0 + i0 * ldr;
+        for (int e = c; e < nr * ldr; e += S_PRODUCERS) rtile[e] = __ldg(src + e);
+        bar_sync(FZ_PBAR, S_PRODUCERS);
+      }
+      if (s >= nstage_d) bar_sync(1 + S_MAXSTAGE + (s % nstage_d), S_THREADS);   // EMPTY[slot] of the DMMA ring
+      double* st = smem + (size_t)(s % nstage_d) * (S_RCH * PITCH) + c;
+      double* arow = a.A + (row0 + row_begin + (int64_t)s * S_RCH) * a.lda + c;
+      const double* rs = rtile + (loads_raw ? srcc : 0);
+      unsigned nf = 0u;
+      if (valid == 0xffffffffu) {
+        // fast path (every stage but a ragged last one): no per-row predicates.  Non-finite detection is one add and
+        // one or per row: (hi & 0x7ff00000) + 0x00100000 has bit 31 set iff the exponent field is all ones.
+        // Explicit 32-bit shared-memory addresses (no generic-pointer arithmetic); no fp64 instruction at all when
+        // blank2J is a mask of ones: the rows go into the ring unweighted, the consumers apply the weights.
+        unsigned acc = 0u;
+        unsigned r_addr = fz_smem_u32(rs);
+        const unsigned s_addr = fz_smem_u32(st);
+        const unsigned ldr8 = (unsigned)ldr * 8u;
+        if (warp_unit_pref) {
+#pragma unroll
+          for (int j = 0; j < S_RCH; ++j) {
+            double x = 0.0;
+            if (loads_raw) x = fz_lds(r_addr);
+            r_addr += ldr8;
+            acc |= ((unsigned)__double2hiint(x) & 0x7ff00000u) + 0x00100000u;
+            if (do_store) arow[0] = x;                             // blank2J == 1: A = R
+            arow += a.lda;
+            if (ring_thread) fz_sts(s_addr + (unsigned)(j * PITCH * 8), x);      // padding columns: x = 0
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < S_RCH; ++j) {
+            double x = 0.0;
+            if (loads_raw) x = fz_lds(r_addr);
+            r_addr += ldr8;
+            acc |= ((unsigned)__double2hiint(x) & 0x7ff00000u) + 0x00100000u;
+            const double val = x * pref;                           // lead columns hold x = 0
+            if (do_store) arow[0] = val;
+            arow += a.lda;
+            if (ring_thread) fz_sts(s_addr + (unsigned)(j * PITCH * 8), val);
+          }
+        }
+        nf = (acc >> 31) ? 0xffffffffu : 0u;                       // which row does not matter below
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < S_RCH; ++j) {
+          const bool ok = (valid >> j) & 1u;
+          const double x = (loads_raw && ok) ? rs[j * ldr] : 0.0;
+          nf |= ((unsigned)__double2hiint(x) & 0x7ff00000u) == 0x7ff00000u ? (1u << j) : 0u;
+          const double val = x * pref;
+          if (do_store && ok) arow[0] = val;
+          arow += a.lda;
+          if (ring_thread) st[j * PITCH] = (acol && ok) ? val : 0.0;
+        }
+      }
+      nf = (loads_raw && acol) ? (nf & valid) : 0u;
+      bad |= nf != 0u;
+      unsigned redo = special;
+      if (do_scrub && __any_sync(0xffffffffu, nf != 0u)) redo = valid;           // numpy.nan_to_num: rare
+      if (redo) {
+        arow = a.A + (row0 + row_begin + (int64_t)s * S_RCH) * a.lda + c;
+#pragma unroll 1
+        for (int j = 0; j < S_RCH; ++j) {
+          if ((redo >> j) & 1u) {                                // warp-uniform
+            const int kind = __shfl_sync(0xffffffffu, dA.kind, j);
+            const double div = __shfl_sync(0xffffffffu, dA.div, j);
+            const int cfg = __shfl_sync(0xffffffffu, dA.cfg, j);
+            if (acol) {
+              const double x = loads_raw ? rs[j * ldr] : 0.0;
+              const double tf = (kind == 0 && !loads_raw) ? __ldg(a.type_fraction + (size_t)cfg * a.numtypes + (-srcc - 1)) : 0.0;
+              const double val = fused_special_row(x, kind, div, tf, pref, loads_raw, do_scrub);
+              if (do_store) arow[(int64_t)j * a.lda] = val;
+              st[j * PITCH] = val;
+            }
+          }
+        }
+      }
+      if (bwarp) {         // the b column of the ring and the weights of the stage's rows (0: test row / past the end)
+        smem[(size_t)(s % nstage_d) * (S_RCH * PITCH) + lane * PITCH + k] = dA.bval;
+        wring[(s % nstage_d) * S_RCH + lane] = dA.wg;
+      }
+      __syncwarp();
+      if (lane == 0)       // this warp is done reading the raw tile
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fz_smem_u32(&raw_empty[rslot])) : "memory");
       __threadfence_block();
-      bar_arrive(1 + (s % NSTAGE), S_THREADS);                               // FULL[slot]
-      rowA = rowB; m2a = m2b; cfg2 = cfgN; tst2 = tstN;
+      bar_arrive(1 + (s % nstage_d), S_THREADS);                               // FULL[slot] of the DMMA ring
+      dA = dB;
     }
     if (a.nonfinite && __any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(a.nonfinite, 1);
     return;
@@ -461,19 +595,25 @@ __global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p)
   const int part = (group == 0) ? (warp & 3) : 3 - (warp & 3);
   constexpr int B1 = part_begin(NB, 1), B2 = part_begin(NB, 2), B3 = part_begin(NB, 3);
   switch (part) {
-    case 0: consume<0, B1>(p.partial, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
-    case 1: consume<B1, B2>(p.partial, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
-    case 2: consume<B2, B3>(p.partial, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
-    default: consume<B3, NB>(p.partial, smem, PITCH, NSTAGE, group, lane, nsteps, cta); break;
+    case 0: consume<0, B1>(p.partial, smem, PITCH, nstage_d, group, lane, nsteps, cta, wring); break;
+    case 1: consume<B1, B2>(p.partial, smem, PITCH, nstage_d, group, lane, nsteps, cta, wring); break;
+    case 2: consume<B2, B3>(p.partial, smem, PITCH, nstage_d, group, lane, nsteps, cta, wring); break;
+    default: consume<B3, NB>(p.partial, smem, PITCH, nstage_d, group, lane, nsteps, cta, wring); break;
   }
 }
 
 template <int NB>
-int launch_fused_nb(const FusedArgs& a, int ncta, cudaStream_t s) {
+int launch_fused_nb(const FusedArgs& a, int ncta, size_t smem_optin, cudaStream_t s) {
   constexpr int PITCH = 8 * NB + 4;
-  const size_t smem = (size_t)ring_depth(NB) * (S_RCH * PITCH) * sizeof(double);
+  const int ldr = a.sc.ncoeff * a.sc.numtypes + 1;
+  const size_t stage_d = (size_t)S_RCH * PITCH * sizeof(double);
+  const size_t raw_b = (size_t)FZ_RAW_STAGES * S_RCH * ldr * sizeof(double);
+  if (smem_optin < raw_b + 2 * stage_d + 2048) return FSB_ERR_UNSUPPORTED;
+  int nstage_d = (int)((smem_optin - 2048 - raw_b) / stage_d);
+  if (nstage_d > S_MAXSTAGE) nstage_d = S_MAXSTAGE;
+  const size_t smem = (size_t)nstage_d * stage_d + raw_b;
   FSB_CUDA_TRY(cudaFuncSetAttribute(scatter_gram_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  scatter_gram_kernel<NB><<<ncta, S_THREADS, smem, s>>>(a);
+  scatter_gram_kernel<NB><<<ncta, S_THREADS, smem, s>>>(a, nstage_d);
   FSB_LAUNCH_CHECK("scatter_gram_kernel");
   return FSB_OK;
 }
@@ -529,17 +669,22 @@ bool fsb_scatter_gram_supported(const ScatterArgs& sc, int64_t total) {
   return !off && (sc.flags & all_rows) == all_rows && sc.row_cfg != nullptr && (k + 1 + 7) / 8 <= 13 && total > 0;
 }
 
+size_t fsb_scatter_gram_desc_bytes(int64_t total) { return (size_t)(total > 0 ? total : 1) * sizeof(FusedDesc); }
+
 int fsb_launch_scatter_gram_small(const fsb_context* h, const ScatterArgs& sc, const uint8_t* testing, int64_t total,
-                                  int store_a, double* partial, cudaStream_t s) {
+                                  int store_a, double* partial, void* desc, cudaStream_t s) {
   const bool bzero = sc.flags & FSB_BZEROFLAG;
   const int k = sc.ncoeff * sc.numtypes + (bzero ? 0 : sc.numtypes);
   const int nb = (k + 1 + 7) / 8;
   FusedArgs a;
   a.sc = sc; a.testing = testing; a.total = total; a.partial = partial; a.store_a = store_a;
+  a.desc = (const FusedDesc*)desc;
+  row_resolve_kernel<<<(unsigned)fsb_ceil_div(total, 256), 256, 0, s>>>(sc, testing, total, (FusedDesc*)desc);
+  FSB_LAUNCH_CHECK("row_resolve_kernel");
   const int want = fsb_gram_small_ctas(h, total);
   a.rows_per_cta = fsb_round_up(fsb_ceil_div(total > 0 ? total : 1, want), S_RCH);
   switch (nb) {
-#define FSB_NB(N) case N: return launch_fused_nb<N>(a, want, s);
+#define FSB_NB(N) case N: return launch_fused_nb<N>(a, want, h->smem_optin, s);
     FSB_NB(1) FSB_NB(2) FSB_NB(3) FSB_NB(4) FSB_NB(5) FSB_NB(6) FSB_NB(7)
     FSB_NB(8) FSB_NB(9) FSB_NB(10) FSB_NB(11) FSB_NB(12) FSB_NB(13)
 #undef FSB_NB
