@@ -517,28 +517,44 @@ __global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p,
         unsigned r_addr = fz_smem_u32(rs);
         const unsigned s_addr = fz_smem_u32(st);
         const unsigned ldr8 = (unsigned)ldr * 8u;
+        // batches of 8 rows: the 8 shared-memory loads are issued back to back, then consumed (one warp per scheduler:
+        // nothing else hides the LDS latency)
         if (warp_unit_pref) {
 #pragma unroll
-          for (int j = 0; j < S_RCH; ++j) {
-            double x = 0.0;
-            if (loads_raw) x = fz_lds(r_addr);
-            r_addr += ldr8;
-            acc |= ((unsigned)__double2hiint(x) & 0x7ff00000u) + 0x00100000u;
-            if (do_store) arow[0] = x;                             // blank2J == 1: A = R
-            arow += a.lda;
-            if (ring_thread) fz_sts(s_addr + (unsigned)(j * PITCH * 8), x);      // padding columns: x = 0
+          for (int j0 = 0; j0 < S_RCH; j0 += 8) {
+            double x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              x[u] = 0.0;
+              if (loads_raw) x[u] = fz_lds(r_addr + (unsigned)u * ldr8);
+            }
+            r_addr += 8u * ldr8;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              acc |= ((unsigned)__double2hiint(x[u]) & 0x7ff00000u) + 0x00100000u;
+              if (do_store) arow[0] = x[u];                          // blank2J == 1: A = R
+              arow += a.lda;
+              if (ring_thread) fz_sts(s_addr + (unsigned)((j0 + u) * PITCH * 8), x[u]);      // padding columns: x = 0
+            }
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < S_RCH; ++j) {
-            double x = 0.0;
-            if (loads_raw) x = fz_lds(r_addr);
-            r_addr += ldr8;
-            acc |= ((unsigned)__double2hiint(x) & 0x7ff00000u) + 0x00100000u;
-            const double val = x * pref;                           // lead columns hold x = 0
-            if (do_store) arow[0] = val;
-            arow += a.lda;
-            if (ring_thread) fz_sts(s_addr + (unsigned)(j * PITCH * 8), val);
+          for (int j0 = 0; j0 < S_RCH; j0 += 8) {
+            double x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              x[u] = 0.0;
+              if (loads_raw) x[u] = fz_lds(r_addr + (unsigned)u * ldr8);
+            }
+            r_addr += 8u * ldr8;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              acc |= ((unsigned)__double2hiint(x[u]) & 0x7ff00000u) + 0x00100000u;
+              const double val = x[u] * pref;                        // lead columns hold x = 0
+              if (do_store) arow[0] = val;
+              arow += a.lda;
+              if (ring_thread) fz_sts(s_addr + (unsigned)((j0 + u) * PITCH * 8), val);
+            }
           }
         }
         nf = (acc >> 31) ? 0xffffffffu : 0u;                       // which row does not matter below
@@ -560,19 +576,18 @@ __global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p,
       if (do_scrub && __any_sync(0xffffffffu, nf != 0u)) redo = valid;           // numpy.nan_to_num: rare
       if (redo) {
         arow = a.A + (row0 + row_begin + (int64_t)s * S_RCH) * a.lda + c;
-#pragma unroll 1
-        for (int j = 0; j < S_RCH; ++j) {
-          if ((redo >> j) & 1u) {                                // warp-uniform
-            const int kind = __shfl_sync(0xffffffffu, dA.kind, j);
-            const double div = __shfl_sync(0xffffffffu, dA.div, j);
-            const int cfg = __shfl_sync(0xffffffffu, dA.cfg, j);
-            if (acol) {
-              const double x = loads_raw ? rs[j * ldr] : 0.0;
-              const double tf = (kind == 0 && !loads_raw) ? __ldg(a.type_fraction + (size_t)cfg * a.numtypes + (-srcc - 1)) : 0.0;
-              const double val = fused_special_row(x, kind, div, tf, pref, loads_raw, do_scrub);
-              if (do_store) arow[(int64_t)j * a.lda] = val;
-              st[j * PITCH] = val;
-            }
+        while (redo) {                                           // warp-uniform: only the rows that need it
+          const int j = __ffs((int)redo) - 1;
+          redo &= redo - 1u;
+          const int kind = __shfl_sync(0xffffffffu, dA.kind, j);
+          const double div = __shfl_sync(0xffffffffu, dA.div, j);
+          const int cfg = __shfl_sync(0xffffffffu, dA.cfg, j);
+          if (acol) {
+            const double x = loads_raw ? rs[j * ldr] : 0.0;
+            const double tf = (kind == 0 && !loads_raw) ? __ldg(a.type_fraction + (size_t)cfg * a.numtypes + (-srcc - 1)) : 0.0;
+            const double val = fused_special_row(x, kind, div, tf, pref, loads_raw, do_scrub);
+            if (do_store) arow[(int64_t)j * a.lda] = val;
+            st[j * PITCH] = val;
           }
         }
       }
