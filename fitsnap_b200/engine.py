@@ -252,7 +252,9 @@ class Engine:
         (rank-deficient fallback, see csrc/pinv.cu)."""
         k = gaug.shape[0] - 1
         if rcond is None:
-            rcond = k * 2.220446049250313e-16
+            # resolution of a Gram formed and diagonalised in fp64: eigenvalues below ~k eps lambda_max are rounding
+            # noise of the Jacobi sweeps as much as of the Gram (a cut at exactly k eps let a null direction through)
+            rcond = 32 * k * 2.220446049250313e-16
         nbytes = self.lib.fsb_pinv_bytes(self._h, k)
         buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         info = torch.zeros(2, dtype=torch.int32, device=self.device)

@@ -286,9 +286,10 @@ class CapturedStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
+        n0 = pipe.engine.launch_count
         with torch.cuda.graph(self.graph):
             self.result = pipe.fit_batch(batch, testing, out)
-        self.launches = self.result.launches + 1      # kernels inside one replay (scatter + the fit)
+        self.launches = pipe.engine.launch_count - n0      # kernels inside one replay (counted by the library)
 
     def replay(self) -> FitResult:
         self.graph.replay()

@@ -184,7 +184,7 @@ class LinearSolverBase:
                    "dependent column %d, %d dropped by the Cholesky factor); switching to the eigenvalue-truncated "
                    "%s solve of the Gram (singular values below ~%.0e sigma_max are cut; scipy's gelsd cuts at 1e-13)"
                    % (self.name, self.info["first_bad_column"], self.info["deficient"],
-                      "minimum-norm" if alpha == 0.0 else "ridge", float(np.sqrt(k * 2.220446049250313e-16))))
+                      "minimum-norm" if alpha == 0.0 else "ridge", float(np.sqrt(32 * k * 2.220446049250313e-16))))
         if not self.min_norm_fallback:
             return res
         res2 = _engine.fit_rows_min_norm(self._engine(), A, B, W, T, res.gaug, refine=3, group=self.process_group,
