@@ -709,8 +709,19 @@ def test_ridge_rank_deficient_falls_back_and_warns(engine):
     r.engine = engine
     r.perform_fit(a=a, b=b, w=w, trainall=True)
     assert r.info["status"] == 1 and msgs and "rank deficient" in msgs[0]
-    ref = lf.ridge_fit_exact(a, b, w, alpha)
-    assert lf.coeff_rel_err(r.fit, ref)[1] < 1e-6
+    # Reference: with exactly dependent columns the ridge minimiser has NO component in the null space of aw (there
+    # aw^T bw vanishes) and differs from the minimum-norm least-squares solution by alpha / sigma_min(range)^2 ~ 1e-13.
+    # The augmented-system solve (ridge_fit_exact) is not usable here: its rounding noise in the null directions is
+    # amplified by sigma / (sigma^2 + alpha) with sigma ~ 1e-14, alpha = 1e-10 (a spurious 1e-4 component, measured;
+    # sklearn's own answer is off by 7e-3 for the same reason).
+    ref = np.linalg.lstsq(a * w[:, None], b * w, rcond=1e-13)[0]
+    assert lf.coeff_rel_err(r.fit, ref)[1] < 1e-9
+    for null in ((2, 7, 1.0, -1.0), (4, 13, 1.0, -1.0)):
+        v = np.zeros(20)
+        v[null[0]], v[null[1]] = null[2], null[3]
+        if null[0] == 4:
+            v[5] = -1.0
+        assert abs(r.fit @ v) / np.linalg.norm(v) < 1e-10 * np.linalg.norm(r.fit)
 
 
 def test_pageable_upload_through_the_pinned_ring(engine):
