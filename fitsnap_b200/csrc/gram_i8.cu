@@ -52,6 +52,15 @@ constexpr int TMEM_COLS = 512;       // two 128 x 256 int32 accumulators
 constexpr int64_t SLAB_ROWS = 262144;   // 2^18: with BETA = 53, 2^18 * 2^106 < P/2
 constexpr int64_t UNIT_ROWS_MAX = 65536;
 constexpr int CV_ROWS = 128, CV_COLS = 32, CV_THREADS = 256;
+// Residue planes: byte (t, c, r) of a slab lives at  (t * kpc + c) * ldr + r  (ldr = slab height).  Modulus-major ON
+// PURPOSE: a column-major variant with constant strides (the 16 stores of a column as immediate offsets) made the
+// conversion 7 % faster and the tensor-core kernel 3.7x SLOWER -- the 128 lines of a TMA box were 4 MB apart, one 2 MB
+// page each, and the units of one (chunk, modulus) touched >1000 pages instead of ~130 (gpurun_out/s4_launches_i8.csv).
+#ifndef FSB_NCW
+#define FSB_NCW 16
+#endif
+constexpr int NCW = FSB_NCW;                 // converter warps riding in the GEMM CTA (two groups of CV_THREADS / 32)
+constexpr int GEMM_THREADS_CV = GEMM_THREADS + 32 * NCW;
 
 struct I8Tables {
   int mod[NMOD];
@@ -136,6 +145,7 @@ constexpr I8Tables make_tables() {
 }
 
 __constant__ I8Tables c_tab = make_tables();
+constexpr I8Tables k_tab = make_tables();      // the same values as compile-time constants (immediates in the converter)
 
 // ------------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -219,9 +229,18 @@ __device__ __forceinline__ unsigned umma_idesc_i8(int m, int n) {
 // column maxima of |w a| over the slab; bit patterns of non-negative doubles order like integers
 __global__ void __launch_bounds__(256) i8_colmax_kernel(const double* __restrict__ A, int64_t lda,
                                                         const double* __restrict__ b,
-                                                        const double* __restrict__ weff, int64_t nrows, int k,
-                                                        int64_t rows_per_cta, unsigned long long* __restrict__ colmax,
+                                                        const double* __restrict__ weff, int64_t nrows_total, int k,
+                                                        int64_t slab_rows, int64_t rows_per_cta,
+                                                        unsigned long long* __restrict__ colmax_all, int colmax_ld,
                                                         int* __restrict__ nonfinite) {
+  // blockIdx.z = slab: all slabs of a Gram in ONE launch, maxima per slab in colmax_all[slab][colmax_ld]
+  const int64_t slab0 = (int64_t)blockIdx.z * slab_rows;
+  int64_t nrows = nrows_total - slab0;
+  if (nrows > slab_rows) nrows = slab_rows;
+  A += slab0 * lda;
+  b += slab0;
+  weff += slab0;
+  unsigned long long* colmax = colmax_all + (size_t)blockIdx.z * colmax_ld;
   const int c = blockIdx.x * 256 + threadIdx.x;
   const int ka = k + 1;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
@@ -270,20 +289,29 @@ template <int T>
 __device__ __forceinline__ void convert_one_modulus(const unsigned (&lo)[4], const unsigned (&hi)[4], unsigned* dst,
                                                     size_t plane_words) {
   constexpr int P = kMods[T];
+  // per-modulus constants as immediates: inside the converter loop of i8_gemm_kernel constant-bank operands would be
+  // hoisted into ~80 registers
+  constexpr int WLO = k_tab.wlo[T], WHI = k_tab.whi[T], OFF = k_tab.off[T], FINIT = k_tab.finit[T];
+  constexpr unsigned MAGIC = k_tab.magic[T];
+  constexpr float FINV = k_tab.finv[T];
   unsigned res[4];   // residue of row q in the low byte
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     if constexpr (P == 256) {          // two's complement low byte
       res[q] = lo[q];
     } else if constexpr (P > 253) {    // 255: no slack for a sloppy quotient, exact integer reduction
-      const unsigned u = (unsigned)dp4a_us(hi[q], c_tab.whi[T], dp4a_us(lo[q], c_tab.wlo[T], c_tab.off[T]));
-      const unsigned qq = __umulhi(u, c_tab.magic[T]);
+      const unsigned u = (unsigned)dp4a_us(hi[q], WHI, dp4a_us(lo[q], WLO, OFF));
+      const unsigned qq = __umulhi(u, MAGIC);
       res[q] = (unsigned)((int)(u - qq * (unsigned)P) - P / 2);
     } else {
-      const float uf = __int_as_float(dp4a_us(hi[q], c_tab.whi[T], dp4a_us(lo[q], c_tab.wlo[T], c_tab.finit[T])));
-      const float qm = __fmaf_rn(uf, c_tab.finv[T], 12582912.0f);
-      const float qq = __fsub_rn(qm, c_tab.fsub[T]);
-      res[q] = (unsigned)__float_as_int(__fmaf_rn(-qq, (float)P, uf));
+      // u = bit pattern of the float uf = T + 2048 p + S (see I8Tables).  qm = 1.5 2^23 + n with n = rint(uf / p) =
+      // T/p + 2048 + rint(S / p); its bit pattern is 0x4B400000 + n.  Only the LOW BYTE of the result is kept, and
+      // T, 2048 p and 0x4B400000 P are multiples of 256: (u - bits(qm) P) mod 256 = (S - P rint(S / p)) mod 256, the
+      // symmetric residue in two's complement -- one integer multiply-add instead of a float subtract and a fused
+      // multiply-add (same n, hence the same residue bytes as the three-float-operation form).
+      const int u = dp4a_us(hi[q], WHI, dp4a_us(lo[q], WLO, FINIT));
+      const float qm = __fmaf_rn(__int_as_float(u), FINV, 12582912.0f);
+      res[q] = (unsigned)(u - __float_as_int(qm) * P);
     }
   }
   const unsigned t01 = __byte_perm(res[0], res[1], 0x0040);
@@ -300,28 +328,40 @@ __device__ __forceinline__ void convert_all_moduli(const unsigned (&lo)[4], cons
 // residue planes: planes[(t * kpc + c) * ldr + r] = (rint(w_r a_rc 2^e_c)) mod p_t, symmetric, int8
 // A warp owns 4 columns x 128 rows: lane l holds rows 4l..4l+3 of each, so every store instruction writes one
 // full 128-byte line of one plane (no shared-memory transpose) and every load fetches whole 32-byte sectors.
-__global__ void __launch_bounds__(CV_THREADS, 3) i8_convert_kernel(const double* __restrict__ A, int64_t lda,
-                                                                  const double* __restrict__ b,
-                                                                  const double* __restrict__ weff, int64_t nrows,
-                                                                  int k, const unsigned long long* __restrict__ colmax,
-                                                                  int beta, unsigned* __restrict__ planes, int64_t ldr,
-                                                                  int kpc) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ka = k + 1;
-  const int c0 = blockIdx.x * CV_COLS + warp * 4;       // first of this warp's 4 columns
-  const int64_t r0 = (int64_t)blockIdx.y * CV_ROWS + lane * 4;
+// Eight warps side by side cover 32 columns = 256 contiguous bytes of every row.
+struct ConvArgs {
+  const double* A;
+  int64_t lda;
+  const double* b;
+  const double* weff;
+  int64_t nrows;                       // rows of this slab
+  int k;
+  const unsigned long long* colmax;    // column maxima of this slab
+  int beta;
+  unsigned* planes;
+  int64_t ldr;                         // rows a plane column holds (slab height, multiple of CV_ROWS)
+  int ncolt;                           // column tiles (kpc / CV_COLS)
+  int ntile;                           // ncolt * row blocks; 0 = nothing to convert
+};
+
+__device__ __forceinline__ void convert_tile(const ConvArgs& cv, int c0, int64_t r0) {
+  const int k = cv.k, ka = cv.k + 1;
+  const size_t col_words = (size_t)cv.ldr / 4, plane_words = (size_t)cv.ncolt * CV_COLS * col_words;
+  unsigned* colbase = cv.planes + (size_t)c0 * col_words + (size_t)r0 / 4;
   if (c0 >= ka) {                                        // padding columns of the last tile: zero residues
     for (int j = 0; j < 4; ++j)
-      for (int t = 0; t < NMOD; ++t) planes[(((size_t)t * kpc + c0 + j) * (size_t)ldr + r0) / 4] = 0u;
+      for (int t = 0; t < NMOD; ++t) colbase[(size_t)t * plane_words + (size_t)j * col_words] = 0u;
     return;
   }
+  const double* __restrict__ A = cv.A;
+  const int64_t lda = cv.lda, nrows = cv.nrows;
   double v[4][4], wv[4];
   const bool vec = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int64_t r = r0 + q;
     const int64_t rc = r < nrows ? r : nrows - 1;         // rows past the end: clamped address, weight 0
-    wv[q] = r < nrows ? __ldg(weff + rc) : 0.0;
+    wv[q] = r < nrows ? __ldg(cv.weff + rc) : 0.0;
     const double* row = A + rc * lda;
     if (vec && c0 + 3 < k) {     // whole 32-byte sector of this row in two 16-byte loads
       const double2 x0 = __ldg(reinterpret_cast<const double2*>(row + c0));
@@ -331,17 +371,16 @@ __global__ void __launch_bounds__(CV_THREADS, 3) i8_convert_kernel(const double*
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c = c0 + j;
-        v[q][j] = (c < k) ? __ldg(row + c) : ((c == k) ? __ldg(b + rc) : 0.0);
+        v[q][j] = (c < k) ? __ldg(row + c) : ((c == k) ? __ldg(cv.b + rc) : 0.0);
       }
     }
   }
-  const size_t plane_words = (size_t)kpc * (size_t)ldr / 4;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = c0 + j;
     double scale = 0.0;
     if (c < ka)   // 2^e, e in [-1000, 1000]: assemble the exponent field directly
-      scale = __longlong_as_double((long long)(scale_exponent(__ldg(colmax + c), beta) + 1023) << 52);
+      scale = __longlong_as_double((long long)(scale_exponent(__ldg(cv.colmax + c), cv.beta) + 1023) << 52);
     unsigned lo[4], hi[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -349,9 +388,14 @@ __global__ void __launch_bounds__(CV_THREADS, 3) i8_convert_kernel(const double*
       lo[q] = (unsigned)iv;
       hi[q] = ((unsigned)((unsigned long long)iv >> 32) & 0x00FFFFFFu) | (iv < 0 ? 0x01000000u : 0u);
     }
-    convert_all_moduli(lo, hi, planes + ((size_t)c * (size_t)ldr + r0) / 4, plane_words,
-                       std::make_integer_sequence<int, NMOD>{});
+    convert_all_moduli(lo, hi, colbase + (size_t)j * col_words, plane_words, std::make_integer_sequence<int, NMOD>{});
   }
+}
+
+// stand-alone conversion (first slab of a Gram; the following slabs are converted inside i8_gemm_kernel)
+__global__ void __launch_bounds__(CV_THREADS, 3) i8_convert_kernel(ConvArgs cv) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  convert_tile(cv, blockIdx.x * CV_COLS + warp * 4, (int64_t)blockIdx.y * CV_ROWS + lane * 4);
 }
 
 // ------------------------------------------------------------------------------------------------ 3
@@ -401,7 +445,15 @@ __device__ __forceinline__ Unit decode_unit(const GemmArgs& p, int unit) {
 // resident from the start, so the block scheduler can place the conversion kernel of the next slab beside them).
 // Two accumulators in TMEM (2 x 256 columns): the epilogue of unit n drains one while the MMAs of unit n+1
 // fill the other.
-__global__ void __launch_bounds__(GEMM_THREADS, 1) i8_gemm_kernel(const __grid_constant__ CUtensorMap tmap, GemmArgs p) {
+//
+// Warps 6.. (present when the launch has GEMM_THREADS_CV threads) are CONVERTERS: while the tensor cores contract the
+// planes of slab s, they turn slab s+1 of the design matrix into the OTHER plane buffer (convert_tile, the code of
+// i8_convert_kernel).  The MMA issuer, the TMA producer and the epilogue warps leave nearly every issue slot of the
+// SM unused, and the conversion needs no shared memory: both halves of the Gram pipeline run at the same time
+// inside one launch, the kernel boundary is the only synchronisation between them.  Column tile fastest, tiles
+// strided over (CTA, converter group): at any moment the whole GPU reads one neighbourhood of rows of A.
+__global__ void __launch_bounds__(GEMM_THREADS_CV, 1) i8_gemm_kernel(const __grid_constant__ CUtensorMap tmap, GemmArgs p,
+                                                                    ConvArgs cv) {
   extern __shared__ __align__(1024) unsigned char gm_sm[];
   __shared__ __align__(8) unsigned long long s_full[NST];
   __shared__ __align__(8) unsigned long long s_empty[NST];
@@ -479,6 +531,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) i8_gemm_kernel(const __grid_c
         }
         tc_commit(smem_u32(&s_acc_full[ab]));    // accumulator complete
       }
+    }
+  } else if (warp >= GEMM_THREADS / 32) {
+    const int cw = warp - GEMM_THREADS / 32;
+    const int grp = cw >> 3, w8 = cw & 7;
+    const int ngrp = (int)(blockDim.x - GEMM_THREADS) / CV_THREADS;
+    for (int tile = (int)blockIdx.x * ngrp + grp; tile < cv.ntile; tile += (int)gridDim.x * ngrp) {
+      const int colt = tile % cv.ncolt, rowb = tile / cv.ncolt;
+      convert_tile(cv, colt * CV_COLS + w8 * 4, (int64_t)rowb * CV_ROWS + lane * 4);
     }
   } else {
     // epilogue: warp w may touch TMEM lanes [32 (w % 4), +32)
@@ -609,9 +669,9 @@ EncodeTiledFn get_encode() {
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct I8Plan {
-  int ka, n_i, ntile, kp, kpc;
-  int64_t slab_rows, ldr;
-  size_t off_colmax, off_flag, off_table, off_planes, total;
+  int ka, n_i, ntile, kp, kpc, ka_pad, nbuf;
+  int64_t slab_rows, nslab;
+  size_t off_colmax, off_flag, off_table, off_planes, plane_bytes, total;
 };
 
 I8Plan plan_i8(int64_t n_rows, int k) {
@@ -622,17 +682,31 @@ I8Plan plan_i8(int64_t n_rows, int k) {
   for (int i = 0; i < pl.n_i; ++i) pl.ntile += i / 2 + 1;
   pl.kp = pl.n_i * BM;
   pl.kpc = (int)fsb_round_up(pl.ka, CV_COLS);
+  pl.ka_pad = (int)fsb_round_up(pl.ka, 32);
   const int64_t n = n_rows > 0 ? n_rows : 1;
-  const int64_t nslab = fsb_ceil_div(n, SLAB_ROWS);
-  pl.slab_rows = fsb_round_up(fsb_ceil_div(n, nslab), CV_ROWS);
-  pl.ldr = pl.slab_rows;
+  pl.nslab = fsb_ceil_div(n, SLAB_ROWS);
+  pl.slab_rows = fsb_round_up(fsb_ceil_div(n, pl.nslab), CV_ROWS);
+  pl.nbuf = pl.nslab > 1 ? 2 : 1;      // slab s+1 is converted while slab s is contracted
   pl.off_colmax = 0;
-  pl.off_flag = align256((size_t)pl.ka * sizeof(unsigned long long));
+  pl.off_flag = align256((size_t)pl.nslab * pl.ka_pad * sizeof(unsigned long long));
   pl.off_table = pl.off_flag + 256;
   size_t off = pl.off_table + align256((size_t)NMOD * pl.kp * pl.kp * sizeof(long long));
   pl.off_planes = (off + 1023) & ~(size_t)1023;
-  pl.total = pl.off_planes + align256((size_t)NMOD * pl.kpc * (size_t)pl.ldr) + 1024;   // + slack to align the base
+  pl.plane_bytes = ((size_t)NMOD * pl.kpc * (size_t)pl.slab_rows + 1023) & ~(size_t)1023;
+  pl.total = pl.off_planes + pl.nbuf * pl.plane_bytes + 1024;   // + slack to align the base
   return pl;
+}
+
+int converter_threads() {             // development switch: FSB_I8_CONVERTERS = 0 (default) | 256 | 512
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FSB_I8_CONVERTERS");
+    v = e ? atoi(e) : 0;
+    if (v < 0) v = 0;
+    v = (v / CV_THREADS) * CV_THREADS;
+    if (v > 32 * NCW) v = 32 * NCW;
+  }
+  return v;
 }
 
 }  // namespace
@@ -642,10 +716,8 @@ bool fsb_gram_i8_available() { return get_encode() != nullptr; }
 size_t fsb_gram_i8_ws_bytes(int64_t n_rows, int k) { return plan_i8(n_rows, k).total; }
 
 // `weff` already carries the test mask (weight 0).  gaug is fully overwritten.  Everything runs on `s`.
-// (A two-stream version that converted slab i+1 beside the tensor-core kernel of slab i was measured: the
-// kernels do share SMs once the GEMM is persistent and both ask for the same shared-memory carve-out, but the
-// conversion then runs at ~40 % speed and the carve-out costs it 20 % when alone -- no net gain, so the slabs
-// are processed back to back.)
+// Per Gram: column maxima of every slab (one launch), conversion of slab 0, then per slab ONE launch that contracts
+// slab s on the tensor cores and converts slab s+1 beside it (converter warps of i8_gemm_kernel), and the CRT.
 int fsb_launch_gram_i8(const fsb_context* h, const double* A, int64_t lda, const double* b, const double* weff,
                        int64_t n_rows, int k, double* gaug, void* ws, size_t ws_bytes, cudaStream_t s) {
   const I8Plan pl = plan_i8(n_rows, k);
@@ -667,34 +739,44 @@ int fsb_launch_gram_i8(const fsb_context* h, const double* A, int64_t lda, const
   }
   const size_t gemm_smem = (size_t)NST * STAGE_BYTES + 1024;
   FSB_CUDA_TRY(cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
-  const int64_t nslab = fsb_ceil_div(n_rows, pl.slab_rows);
-  for (int64_t i = 0; i < nslab; ++i) {
+  const int64_t nslab = pl.nslab;
+  FSB_CUDA_TRY(cudaMemsetAsync(colmax, 0, (size_t)nslab * pl.ka_pad * sizeof(unsigned long long), s));
+  {
+    const int64_t nr = n_rows < pl.slab_rows ? n_rows : pl.slab_rows;
+    int64_t rb = fsb_ceil_div(nr, fsb_ceil_div((int64_t)h->sm_count * 8, fsb_ceil_div(ka, 256) * nslab));
+    rb = fsb_round_up(rb < 64 ? 64 : rb, 8);
+    dim3 grid((unsigned)fsb_ceil_div(ka, 256), (unsigned)fsb_ceil_div(nr, rb), (unsigned)nslab);
+    i8_colmax_kernel<<<grid, 256, 0, s>>>(A, lda, b, weff, n_rows, k, pl.slab_rows, rb, colmax, pl.ka_pad, flag);
+    FSB_LAUNCH_CHECK("i8_colmax_kernel");
+  }
+  auto conv_args = [&](int64_t i) {
+    ConvArgs cv;
     const int64_t r0 = i * pl.slab_rows;
-    const int64_t nr = (n_rows - r0) < pl.slab_rows ? (n_rows - r0) : pl.slab_rows;
-    const double* As = A + r0 * lda;
-    const double* bs = b + r0;
-    const double* ws_ = weff + r0;
-    FSB_CUDA_TRY(cudaMemsetAsync(colmax, 0, (size_t)ka * sizeof(unsigned long long), s));
-    {
-      int64_t rb = fsb_ceil_div(nr, fsb_ceil_div((int64_t)h->sm_count * 8, fsb_ceil_div(ka, 256)));
-      rb = fsb_round_up(rb < 64 ? 64 : rb, 8);
-      dim3 grid((unsigned)fsb_ceil_div(ka, 256), (unsigned)fsb_ceil_div(nr, rb));
-      i8_colmax_kernel<<<grid, 256, 0, s>>>(As, lda, bs, ws_, nr, k, rb, colmax, flag);
-      FSB_LAUNCH_CHECK("i8_colmax_kernel");
-    }
-    {
-      dim3 grid((unsigned)(pl.kpc / CV_COLS), (unsigned)fsb_ceil_div(nr, CV_ROWS));
-      i8_convert_kernel<<<grid, CV_THREADS, 0, s>>>(As, lda, bs, ws_, nr, k, colmax, beta, (unsigned*)planes, pl.ldr,
-                                                    pl.kpc);
+    cv.A = A + r0 * lda; cv.lda = lda; cv.b = b + r0; cv.weff = weff + r0;
+    cv.nrows = (n_rows - r0) < pl.slab_rows ? (n_rows - r0) : pl.slab_rows;
+    cv.k = k; cv.colmax = colmax + (size_t)i * pl.ka_pad; cv.beta = beta;
+    cv.planes = (unsigned*)(planes + (size_t)(i % pl.nbuf) * pl.plane_bytes);
+    cv.ldr = pl.slab_rows;
+    cv.ncolt = pl.kpc / CV_COLS;
+    cv.ntile = cv.ncolt * (int)fsb_ceil_div(cv.nrows, CV_ROWS);
+    return cv;
+  };
+  const int cv_threads = converter_threads();
+  for (int64_t i = 0; i < nslab; ++i) {
+    const ConvArgs cur = conv_args(i);
+    const int64_t nr = cur.nrows;
+    if (i == 0 || cv_threads == 0) {
+      dim3 grid((unsigned)cur.ncolt, (unsigned)fsb_ceil_div(nr, CV_ROWS));
+      i8_convert_kernel<<<grid, CV_THREADS, 0, s>>>(cur);
       FSB_LAUNCH_CHECK("i8_convert_kernel");
     }
     {
       CUtensorMap tmap;
       const cuuint64_t gdim[3] = {(cuuint64_t)nr, (cuuint64_t)pl.kpc, (cuuint64_t)NMOD};
-      const cuuint64_t gstr[2] = {(cuuint64_t)pl.ldr, (cuuint64_t)pl.ldr * (cuuint64_t)pl.kpc};
+      const cuuint64_t gstr[2] = {(cuuint64_t)pl.slab_rows, (cuuint64_t)pl.slab_rows * (cuuint64_t)pl.kpc};
       const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1};
       const cuuint32_t estr[3] = {1, 1, 1};
-      CUresult cr = get_encode()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes, gdim, gstr, box, estr,
+      CUresult cr = get_encode()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)cur.planes, gdim, gstr, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (cr != CUDA_SUCCESS) return FSB_ERR_UNSUPPORTED;
@@ -709,12 +791,22 @@ int fsb_launch_gram_i8(const fsb_context* h, const double* A, int64_t lda, const
       const int64_t nchunk = fsb_ceil_div(nr, ur);
       ga.nunits = (int)(nchunk * NMOD * pl.ntile);
       const int grid = ga.nunits < h->sm_count ? ga.nunits : h->sm_count;
-      i8_gemm_kernel<<<(unsigned)grid, GEMM_THREADS, gemm_smem, s>>>(tmap, ga);
+      ConvArgs next;
+      next.ntile = 0;
+      int threads = GEMM_THREADS;
+      if (i + 1 < nslab && cv_threads > 0) {
+        next = conv_args(i + 1);
+        threads = GEMM_THREADS + cv_threads;
+      } else {
+        next = cur;
+        next.ntile = 0;
+      }
+      i8_gemm_kernel<<<(unsigned)grid, (unsigned)threads, gemm_smem, s>>>(tmap, ga, next);
       FSB_LAUNCH_CHECK("i8_gemm_kernel");
     }
     {
       dim3 grid((unsigned)fsb_ceil_div(ka, 128), (unsigned)ka);
-      i8_crt_kernel<<<grid, 128, 0, s>>>(table, pl.kp, ka, colmax, beta, flag, i == 0 ? 1 : 0, gaug);
+      i8_crt_kernel<<<grid, 128, 0, s>>>(table, pl.kp, ka, cur.colmax, beta, flag, i == 0 ? 1 : 0, gaug);
       FSB_LAUNCH_CHECK("i8_crt_kernel");
     }
   }

@@ -146,6 +146,121 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(FactorView f, int p, do
   }
 }
 
+// Cholesky of the 64x64 diagonal block of panel p AND its inverse, one CTA, compact loops.
+// (The first version -- potrf_diag_kernel above, right-looking with three block barriers per column, followed by
+// trsm_panel_kernel / trtri_diag_kernel whose fully unrolled 64-step substitutions run ONCE per launch -- spent
+// 64 + 42 us per panel at k = 1000 (profiles/r02_launches_bench_default.csv): barrier latency in the first,
+// instruction-cache misses on ~6000 straight-line instructions in the other two.)
+//   factor : left-looking.  Thread (r, q), q = tid % 4: the dot of rows r and j over the columns c < j, c = q mod 4,
+//            and the same for the pivot (row j with itself, a broadcast read); two shuffle levels combine the four
+//            parts.  New diagonal entries go to their own array, so ONE block barrier per column suffices.
+//   inverse: X = L^-1 row by row: X[r][j] = -(1 / L[r][r]) sum_{c = j}^{r-1} L[r][c] X[c][j], all 64 columns at once
+//            (thread (j, q) takes the c = q mod 4 part).  Written to the diagonal block of f.Linv: the panel solve
+//            becomes a 64x64x64 product (trsm_gemm_kernel) and trtri_diag_kernel is not needed any more.
+__global__ void __launch_bounds__(256) potrf_inv_kernel(FactorView f, int p, double tol, int32_t* info) {
+  extern __shared__ double pi_sm[];             // s[NB][NBP] | xinv[NB][NBP]: 66.6 KB, dynamic (above the static limit)
+  double (*s)[NBP] = reinterpret_cast<double (*)[NBP]>(pi_sm);
+  double (*xinv)[NBP] = reinterpret_cast<double (*)[NBP]>(pi_sm + NB * NBP);
+  __shared__ double diag[NB], rdiag[NB];
+  __shared__ int dropped[NB];
+  const int kp = f.kp, tid = threadIdx.x;
+  double* blk = f.L + (size_t)(p * NB) * kp + p * NB;
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx / NB, c = idx % NB;
+    s[r][c] = (c <= r) ? blk[(size_t)r * kp + c] : 0.0;
+    xinv[r][c] = 0.0;
+  }
+  __syncthreads();
+  const int r = tid >> 2, q = tid & 3;
+  // diag(S) lies in [0.5, 2) after equilibration, so `tol` is an absolute pivot threshold.
+  for (int j = 0; j < NB; ++j) {
+    double dr = 0.0, dp = 0.0;
+    for (int c = q; c < j; c += 4) {
+      const double lj = s[j][c];
+      dr += s[r][c] * lj;
+      dp += lj * lj;
+    }
+    dr += __shfl_xor_sync(0xffffffffu, dr, 1);
+    dp += __shfl_xor_sync(0xffffffffu, dp, 1);
+    dr += __shfl_xor_sync(0xffffffffu, dr, 2);
+    dp += __shfl_xor_sync(0xffffffffu, dp, 2);
+    const double piv = s[j][j] - dp;
+    const bool drop = !(piv > tol);
+    const double ljj = drop ? 1.0 : sqrt(piv);
+    const double rl = 1.0 / ljj;
+    if (q == 0) {
+      if (r > j) s[r][j] = drop ? 0.0 : (s[r][j] - dr) * rl;
+      if (r == j) { diag[j] = ljj; rdiag[j] = rl; dropped[j] = drop ? 1 : 0; }
+    }
+    __syncthreads();
+  }
+  // inverse, row by row (row r of X needs rows j..r-1)
+  const int jc = tid >> 2;                       // column of X owned by this group of four lanes
+  for (int rr = 0; rr < NB; ++rr) {
+    double acc = 0.0;
+    for (int c = jc + q; c < rr; c += 4) acc += s[rr][c] * xinv[c][jc];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (q == 0 && jc <= rr) xinv[rr][jc] = (jc == rr) ? rdiag[rr] : -rdiag[rr] * acc;
+    __syncthreads();
+  }
+  double* out = f.Linv + (size_t)(p * NB) * f.kp2 + p * NB;
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int rr = idx / NB, c = idx % NB;
+    if (c <= rr) blk[(size_t)rr * kp + c] = (c == rr) ? diag[rr] : s[rr][c];
+    out[(size_t)rr * f.kp2 + c] = xinv[rr][c];
+  }
+  if (tid < NB && dropped[tid]) {
+    const int col = p * NB + tid;
+    f.flag[col] = 1.0;
+    f.d[col] = 0.0;
+    atomicAdd(&info[FSB_INFO_NUM_DEFICIENT], 1);
+    atomicExch(&info[FSB_INFO_STATUS], 1);
+    atomicMin(&info[FSB_INFO_FIRST_BAD_COLUMN], col);
+  }
+}
+
+// Panel solve as a product: L[bi][p] <- A[bi][p] * Linv_pp^T (columns of dropped pivots forced to 0), in place.
+__global__ void __launch_bounds__(256) trsm_gemm_kernel(FactorView f, int p) {
+  constexpr int MH = 32;
+  __shared__ double la[NB][MH + 1];
+  __shared__ double lb[NB][MH + 1];
+  const int kp = f.kp;
+  const int bi = p + 1 + blockIdx.x;
+  double* pa = f.L + (size_t)(bi * NB) * kp + p * NB;
+  const double* pb = f.Linv + (size_t)(p * NB) * f.kp2 + p * NB;
+  const int tr = (threadIdx.x / 16) * 4, tc = (threadIdx.x % 16) * 4;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int mh = 0; mh < NB; mh += MH) {
+    for (int idx = threadIdx.x; idx < NB * MH; idx += blockDim.x) {
+      const int r = idx / MH, c = idx % MH;
+      la[r][c] = pa[(size_t)r * kp + mh + c];
+      lb[r][c] = pb[(size_t)r * f.kp2 + mh + c];
+    }
+    __syncthreads();
+    for (int m = 0; m < MH; ++m) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = la[tr + i][m]; b[i] = lb[tc + i][m]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool dead = f.flag[p * NB + tc + j] != 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pa[(size_t)(tr + i) * kp + tc + j] = dead ? 0.0 : acc[i][j];
+  }
+}
+
 // Panel solve: rows of block-row bi (> p) against L_pp^T.  One thread per row, row in registers.
 __global__ void __launch_bounds__(NB) trsm_panel_kernel(FactorView f, int p) {
   __shared__ double lpp[NB][NBP];
@@ -713,21 +828,40 @@ int fsb_launch_factor(const fsb_context* h, const double* gaug, int k, double al
   FSB_LAUNCH_CHECK("equilibrate_kernel");
   const int np = f.kp / NB;
   const double tol = 64.0 * (double)f.kp * DBL_EPSILON;
+  const bool v1 = getenv("FSB_FACTOR_PANEL_V1") != nullptr;    // first-generation panel kernels, kept for cross-checks
+  const size_t potrf_smem = (size_t)2 * NB * NBP * sizeof(double);
+  if (!v1) {
+    FSB_CUDA_TRY(cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem));
+    FSB_CUDA_TRY(cudaMemsetAsync(f.Linv, 0, (size_t)f.kp2 * f.kp2 * sizeof(double), s));
+  }
   for (int p = 0; p < np; ++p) {
-    potrf_diag_kernel<<<1, 256, 0, s>>>(f, p, tol, info);
-    FSB_LAUNCH_CHECK("potrf_diag_kernel");
     const int rem = np - p - 1;
+    if (v1) {
+      potrf_diag_kernel<<<1, 256, 0, s>>>(f, p, tol, info);
+      FSB_LAUNCH_CHECK("potrf_diag_kernel");
+      if (rem > 0) {
+        trsm_panel_kernel<<<rem, NB, 0, s>>>(f, p);
+        FSB_LAUNCH_CHECK("trsm_panel_kernel");
+      }
+    } else {
+      potrf_inv_kernel<<<1, 256, potrf_smem, s>>>(f, p, tol, info);
+      FSB_LAUNCH_CHECK("potrf_inv_kernel");
+      if (rem > 0) {
+        trsm_gemm_kernel<<<rem, 256, 0, s>>>(f, p);
+        FSB_LAUNCH_CHECK("trsm_gemm_kernel");
+      }
+    }
     if (rem > 0) {
-      trsm_panel_kernel<<<rem, NB, 0, s>>>(f, p);
-      FSB_LAUNCH_CHECK("trsm_panel_kernel");
       syrk_update_kernel<<<rem * (rem + 1) / 2, 256, 0, s>>>(f, p);
       FSB_LAUNCH_CHECK("syrk_update_kernel");
     }
   }
-  // explicit inverse of L by block doubling
-  FSB_CUDA_TRY(cudaMemsetAsync(f.Linv, 0, (size_t)f.kp2 * f.kp2 * sizeof(double), s));
-  trtri_diag_kernel<<<np, NB, 0, s>>>(f);
-  FSB_LAUNCH_CHECK("trtri_diag_kernel");
+  // explicit inverse of L by block doubling (the diagonal blocks are already inverted)
+  if (v1) {
+    FSB_CUDA_TRY(cudaMemsetAsync(f.Linv, 0, (size_t)f.kp2 * f.kp2 * sizeof(double), s));
+    trtri_diag_kernel<<<np, NB, 0, s>>>(f);
+    FSB_LAUNCH_CHECK("trtri_diag_kernel");
+  }
   for (int nb = 1; nb * NB < f.kp2; nb *= 2) {
     const int pairs = f.kp2 / (2 * nb * NB);
     dim3 grid((unsigned)(nb * nb), (unsigned)pairs);

@@ -225,10 +225,13 @@ __global__ void __launch_bounds__(BK_THREADS, 1) rowpass_bulk_kernel(const doubl
       wv = (testing && __ldg(testing + r)) ? 0.0 : ww;
     }
   };
-  double w_cur, b_cur, w_nxt, b_nxt;
+  // two tiles ahead: one tile (~1 us at full rate) does not cover the latency of these dependent global loads -- the
+  // consumers' top stall was long_scoreboard, 2.1 warps per issue slot (profiles/r02_rowpass_c2.txt)
+  double w_cur, b_cur, w_nxt, b_nxt, w_nx2, b_nx2;
   fetch(0, w_cur, b_cur);
+  fetch(1, w_nxt, b_nxt);
   for (int t = 0; t < ntile; ++t) {
-    fetch(t + 1, w_nxt, b_nxt);
+    fetch(t + 2, w_nx2, b_nx2);
     const int slot = t % nstage, n = t / nstage;
     bk_mbar_wait(bk_smem_u32(&s_full[slot]), (unsigned)(n & 1));
     const double* tile = ring + slot * stage_doubles + (size_t)(warp * BK_RPW) * k;
@@ -271,6 +274,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) rowpass_bulk_kernel(const doubl
     if (lane == 0)
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bk_smem_u32(&s_empty[slot])) : "memory");
     w_cur = w_nxt; b_cur = b_nxt;
+    w_nxt = w_nx2; b_nxt = b_nx2;
   }
 
   // fixed-order reduction over the consumer warps (the ring is free now: all tiles consumed by this warp,

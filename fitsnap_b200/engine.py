@@ -77,7 +77,13 @@ class HostStager:
         self.slots = [torch.empty(self.SLOT_BYTES, dtype=torch.uint8).pin_memory() for _ in range(self.NSLOT)]
         self.events = [None] * self.NSLOT
         self.next = 0
-        nthr = max(1, min(8, (os.cpu_count() or 2) // 2))
+        # the fill (pageable -> pinned memcpy) is the slow half of the pipeline (34 GB/s with 8 threads on a 16-core
+        # host against 55 GB/s of PCIe): use the cores this process may run on, less two for Python and the driver
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            ncpu = os.cpu_count() or 2
+        nthr = max(1, min(16, ncpu - 2))
         self.pool = ThreadPoolExecutor(max_workers=nthr)
         self.nthr = nthr
 
@@ -92,8 +98,9 @@ class HostStager:
         for f in futs:
             f.result()
 
-    def upload(self, a, dtype):
-        out = torch.empty(a.shape, dtype=dtype, device=self.device)
+    def upload(self, a, dtype, out=None):
+        if out is None:
+            out = torch.empty(a.shape, dtype=dtype, device=self.device)
         src = a.reshape(-1).view(np.uint8)
         dst = out.view(-1).view(torch.uint8)
         stream = torch.cuda.current_stream(self.device)
@@ -197,6 +204,21 @@ class Engine:
         if self._stager is None:
             self._stager = HostStager(self.device)
         return self._stager.upload(a, dtype)
+
+    def upload_into(self, dst, arr):
+        """Host numpy (same dtype, C-contiguous) -> an existing contiguous device tensor, on the current stream:
+        straight onto the copy engine when the source is pinned, through the pinned ring otherwise."""
+        a = np.ascontiguousarray(arr)
+        assert dst.is_contiguous() and a.dtype == _NP_OF_TORCH[dst.dtype] and a.size == dst.numel()
+        if a.nbytes == 0:
+            return dst
+        t = torch.from_numpy(a)
+        if t.is_pinned() or a.nbytes < HostStager.SMALL:
+            dst.copy_(t.view(dst.shape), non_blocking=True)
+            return dst
+        if self._stager is None:
+            self._stager = HostStager(self.device)
+        return self._stager.upload(a, dst.dtype, out=dst)
 
     @staticmethod
     def _check_matrix(A, b, w, testing):

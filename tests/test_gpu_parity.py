@@ -557,6 +557,28 @@ def test_lasso_matches_tightly_converged_sklearn(engine, ta):
     assert lf.lasso_objective(aw, bw, s2.fit, 1e-6) <= lf.lasso_objective(aw, bw, ta["ref_lasso_1e6"], 1e-6) * (1 + 1e-9)
 
 
+def test_lasso_apply_transpose_matches_sklearn_on_the_normal_system(engine):
+    """[EXTRAS] apply_transpose with LASSO (lasso.py:22-24): sklearn then minimises 1/(2k)|aw^T bw - aw^T aw x|^2 +
+    alpha |x|_1, i.e. the k x k normal matrix is the DESIGN matrix.  The drop-in forms the Gram of (G, c) on the device
+    and runs the same coordinate descent; compared with sklearn iterated to tol 1e-14 on the oracle's statement."""
+    from types import SimpleNamespace
+    from fitsnap_b200.solvers import LASSO
+    a, b, w, t = synth_system(**SOLVE_CASES["well"])
+    alpha = 1.0e3                                      # the normal system has entries ~1e6: this keeps 21 of 37
+    cfg = SimpleNamespace(sections={"LASSO": SimpleNamespace(alpha=alpha, max_iter=200000),
+                                    "EXTRAS": SimpleNamespace(apply_transpose=1)})
+    s = LASSO("LASSO", _pt(a, b, w, t), cfg)
+    s.engine = engine
+    s.perform_fit()
+    tight = lf.lasso_fit(a, b, w, alpha, 200000, t, apply_transpose=True, tol=1e-14)
+    assert s.info["not_converged"] == 0
+    assert np.array_equal(s.fit != 0, tight != 0) and 0 < np.count_nonzero(tight) < len(tight)
+    assert np.max(np.abs(s.fit - tight)) < 1e-7 * np.max(np.abs(tight))
+    # and it is a different minimiser from the tall-system LASSO with the same alpha (the branch is really taken)
+    plain = lf.lasso_fit(a, b, w, alpha, 200000, t, tol=1e-14)
+    assert np.max(np.abs(plain - tight)) > 1e-3 * np.max(np.abs(tight))
+
+
 def test_group_stats_and_ta_metrics_golden(engine, ta):
     """Device error sums -> the numbers of the reference's golden Ta_metrics.md ('*ALL', Unweighted,
     Training, Energy: MAE 0.112787, RMSE 0.379769) and, per group, numpy on the host."""
