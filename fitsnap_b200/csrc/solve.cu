@@ -173,32 +173,56 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(FactorView f, int p, dou
   __syncthreads();
   const int r = tid >> 2, q = tid & 3;
   // diag(S) lies in [0.5, 2) after equilibration, so `tol` is an absolute pivot threshold.
+  // The dots run over a FIXED 16 slots per thread (column q + 4 i, predicated on < j): all shared-memory loads of a
+  // step are issued back to back instead of one dependent load -> multiply-add pair per iteration.
   for (int j = 0; j < NB; ++j) {
-    double dr = 0.0, dp = 0.0;
-    for (int c = q; c < j; c += 4) {
-      const double lj = s[j][c];
-      dr += s[r][c] * lj;
-      dp += lj * lj;
+    double lj[NB / 4], lr[NB / 4];
+#pragma unroll
+    for (int i = 0; i < NB / 4; ++i) {
+      const int c = q + 4 * i;
+      lj[i] = (c < j) ? s[j][c] : 0.0;
+      lr[i] = (c < j) ? s[r][c] : 0.0;
     }
+    double dr0 = 0.0, dr1 = 0.0, dp0 = 0.0, dp1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NB / 4; i += 2) {
+      dr0 += lr[i] * lj[i];
+      dp0 += lj[i] * lj[i];
+      dr1 += lr[i + 1] * lj[i + 1];
+      dp1 += lj[i + 1] * lj[i + 1];
+    }
+    double dr = dr0 + dr1, dp = dp0 + dp1;
     dr += __shfl_xor_sync(0xffffffffu, dr, 1);
     dp += __shfl_xor_sync(0xffffffffu, dp, 1);
     dr += __shfl_xor_sync(0xffffffffu, dr, 2);
     dp += __shfl_xor_sync(0xffffffffu, dp, 2);
     const double piv = s[j][j] - dp;
     const bool drop = !(piv > tol);
-    const double ljj = drop ? 1.0 : sqrt(piv);
-    const double rl = 1.0 / ljj;
+    const double rl = drop ? 1.0 : rsqrt(piv);         // one reciprocal square root instead of sqrt + division
+    const double ljj = drop ? 1.0 : piv * rl;
     if (q == 0) {
       if (r > j) s[r][j] = drop ? 0.0 : (s[r][j] - dr) * rl;
       if (r == j) { diag[j] = ljj; rdiag[j] = rl; dropped[j] = drop ? 1 : 0; }
     }
     __syncthreads();
   }
-  // inverse, row by row (row r of X needs rows j..r-1)
+  // inverse, row by row (row r of X needs rows j..r-1); same fixed-slot dots: c = jc + q + 4 i < rr
   const int jc = tid >> 2;                       // column of X owned by this group of four lanes
   for (int rr = 0; rr < NB; ++rr) {
-    double acc = 0.0;
-    for (int c = jc + q; c < rr; c += 4) acc += s[rr][c] * xinv[c][jc];
+    double a0 = 0.0, a1 = 0.0;
+    double ls[NB / 4], xs[NB / 4];
+#pragma unroll
+    for (int i = 0; i < NB / 4; ++i) {
+      const int c = jc + q + 4 * i;
+      ls[i] = (c < rr) ? s[rr][c] : 0.0;
+      xs[i] = (c < rr) ? xinv[c][jc] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < NB / 4; i += 2) {
+      a0 += ls[i] * xs[i];
+      a1 += ls[i + 1] * xs[i + 1];
+    }
+    double acc = a0 + a1;
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     if (q == 0 && jc <= rr) xinv[rr][jc] = (jc == rr) ? rdiag[rr] : -rdiag[rr] * acc;
@@ -567,7 +591,11 @@ __global__ void __launch_bounds__(512) small_factor_kernel(const double* __restr
 // the diagonal blocks precomputed by small_factor_kernel a substitution is 4 block steps, each two
 // tiny mat-vecs done by the whole CTA (4 threads per row, shuffle-combined), instead of k dependent
 // scalar steps.  128 threads: thread t -> row (t >> 2) of the current block, quarter (t & 3).
-__global__ void __launch_bounds__(SMALL_K) small_solve_kernel(FactorView f, int k, const double* __restrict__ rhs,
+// Launched with SOLVE_THREADS threads: all of them stage the factor (the load phase was most of this kernel when 128
+// threads fetched 131 KB with 8 scalar loads in flight each), the first SMALL_K then run the block substitution on a
+// named barrier of their own and the rest leave.
+constexpr int SOLVE_THREADS = 512;
+__global__ void __launch_bounds__(SOLVE_THREADS) small_solve_kernel(FactorView f, int k, const double* __restrict__ rhs,
                                                               int64_t rhs_stride, double alpha,
                                                               const double* __restrict__ x_in,
                                                               double* __restrict__ x_out) {
@@ -580,12 +608,19 @@ __global__ void __launch_bounds__(SMALL_K) small_solve_kernel(FactorView f, int 
   double* tb = y + kp;                   // 32 (block right-hand side)
   const int tid = threadIdx.x, nt = blockDim.x;
   {
-    const int nel = kp * kp;
-#pragma unroll 8
-    for (int idx = tid; idx < nel; idx += nt) {
-      const int r = idx / kp, c = idx - r * kp;
-      const double v = __ldg(f.L + idx);
-      if (c <= r) L[r * P + c] = v;
+    // lower-triangular 32 x 32 tiles only, 16-byte loads (kp is a multiple of 64: rows are 16-byte aligned)
+    const int nb = kp / 32;
+    const int ntile = nb * (nb + 1) / 2;
+    const double2* L2 = reinterpret_cast<const double2*>(f.L);
+#pragma unroll 4
+    for (int idx = tid; idx < ntile * 512; idx += nt) {
+      const int t = idx >> 9, e = idx & 511;
+      int tr = 0, rem = t;
+      while (rem > tr) { rem -= tr + 1; ++tr; }          // tile (tr, rem), rem <= tr
+      const int r = tr * 32 + (e >> 4), c = rem * 32 + 2 * (e & 15);
+      const double2 v = __ldg(L2 + ((size_t)r * kp + c) / 2);
+      if (c <= r) L[r * P + c] = v.x;
+      if (c + 1 <= r) L[r * P + c + 1] = v.y;
     }
     const int nli = (kp / 32) * 1024;
 #pragma unroll 4
@@ -600,6 +635,8 @@ __global__ void __launch_bounds__(SMALL_K) small_solve_kernel(FactorView f, int 
     y[i] = v;
   }
   __syncthreads();
+  if (tid >= SMALL_K) return;
+#define FSB_SOLVE_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(SMALL_K) : "memory")
   const int nb32 = kp / 32;
   const int row = tid >> 2, q = tid & 3;     // 32 rows x 4 quarters
   // ---- forward: L y = r
@@ -611,14 +648,14 @@ __global__ void __launch_bounds__(SMALL_K) small_solve_kernel(FactorView f, int 
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
     if (q == 0) tb[row] = y[gi] - part;
-    __syncthreads();
+    FSB_SOLVE_SYNC();
     double acc = 0.0;
     for (int m = q; m <= row; m += 4) acc += Li[(b * 32 + row) * 33 + m] * tb[m];
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    __syncthreads();                         // everyone is done reading tb / y of this block
+    FSB_SOLVE_SYNC();                         // everyone is done reading tb / y of this block
     if (q == 0) y[gi] = (gi < k && f.flag[gi] != 0.0) ? 0.0 : acc;
-    __syncthreads();
+    FSB_SOLVE_SYNC();
   }
   // ---- backward: L^T z = y
   for (int b = nb32 - 1; b >= 0; --b) {
@@ -628,16 +665,17 @@ __global__ void __launch_bounds__(SMALL_K) small_solve_kernel(FactorView f, int 
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
     if (q == 0) tb[row] = y[gi] - part;
-    __syncthreads();
+    FSB_SOLVE_SYNC();
     double acc = 0.0;
     for (int m = row + q; m < 32; m += 4) acc += Li[(b * 32 + m) * 33 + row] * tb[m];   // (Linv^T)[row][m]
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    __syncthreads();
+    FSB_SOLVE_SYNC();
     if (q == 0) y[gi] = acc;
-    __syncthreads();
+    FSB_SOLVE_SYNC();
   }
-  for (int i = tid; i < k; i += nt) x_out[i] = (x_in ? x_in[i] : 0.0) + f.d[i] * y[i];
+  for (int i = tid; i < k; i += SMALL_K) x_out[i] = (x_in ? x_in[i] : 0.0) + f.d[i] * y[i];
+#undef FSB_SOLVE_SYNC
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -881,7 +919,7 @@ int fsb_launch_factor_solve(const fsb_context* h, const void* factor, int k, con
     const int kp_s = f.kp, P = kp_s | 1;
     const size_t smem_s = ((size_t)kp_s * P + (size_t)(kp_s / 32) * 32 * 33 + kp_s + 32) * sizeof(double);
     FSB_CUDA_TRY(cudaFuncSetAttribute(small_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-    small_solve_kernel<<<1, SMALL_K, smem_s, s>>>(f, k, rhs, rhs_stride, alpha, x_in, x_out);
+    small_solve_kernel<<<1, SOLVE_THREADS, smem_s, s>>>(f, k, rhs, rhs_stride, alpha, x_in, x_out);
     FSB_LAUNCH_CHECK("small_solve_kernel");
     return FSB_OK;
   }

@@ -159,7 +159,13 @@ __device__ __forceinline__ void bk_mbar_wait(unsigned bar, unsigned parity) {
   __trap();
 }
 
-template <int NPL>
+// Consumer layout (round 2): EIGHT lanes per row, four rows per warp instruction.  Lane (rs = lane / 8, cl = lane % 8)
+// owns the column pairs 2 cl + 16 i of row rs of the current group of four rows: one 16-byte shared-memory load per
+// pair, the dot product needs three shuffle levels (8 lanes) instead of five, every lane slot carries a real column
+// (100 columns on 7 x 16 slots instead of 4 x 32), and the four row groups keep separate column sums that are combined
+// once at the end.  79 -> ~20 warp instructions per row: the consumers were the limit of this kernel (4.8 TB/s with
+// 42 % issue utilisation and two warps per scheduler, profiles/r02_rowpass_c2.txt), not the bulk copies.
+template <int NI>
 __global__ void __launch_bounds__(BK_THREADS, 1) rowpass_bulk_kernel(const double* __restrict__ A,
                                                                      const double* __restrict__ b,
                                                                      const double* __restrict__ w,
@@ -208,12 +214,14 @@ __global__ void __launch_bounds__(BK_THREADS, 1) rowpass_bulk_kernel(const doubl
   }
 
   // ---- consumers
-  double xr[NPL], gacc[NPL];
+  const int rs = lane >> 3, cl = lane & 7;
+  double x0[NI], x1[NI], g0[NI], g1[NI];
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    const int c = lane + 32 * i;
-    xr[i] = (c < k) ? x[c] : 0.0;
-    gacc[i] = 0.0;
+  for (int i = 0; i < NI; ++i) {
+    const int c = 2 * cl + 16 * i;                   // k is even: a pair is inside or outside as a whole
+    x0[i] = (c < k) ? x[c] : 0.0;
+    x1[i] = (c < k) ? x[c + 1] : 0.0;
+    g0[i] = 0.0; g1[i] = 0.0;
   }
   // lane q < BK_RPW keeps (w, b) of row BK_RPW * warp + q of the tile; test rows and rows past the end get w = 0
   auto fetch = [&](int t, double& wv, double& bv) {
@@ -225,49 +233,49 @@ __global__ void __launch_bounds__(BK_THREADS, 1) rowpass_bulk_kernel(const doubl
       wv = (testing && __ldg(testing + r)) ? 0.0 : ww;
     }
   };
-  // two tiles ahead: one tile (~1 us at full rate) does not cover the latency of these dependent global loads -- the
-  // consumers' top stall was long_scoreboard, 2.1 warps per issue slot (profiles/r02_rowpass_c2.txt)
   double w_cur, b_cur, w_nxt, b_nxt, w_nx2, b_nx2;
   fetch(0, w_cur, b_cur);
   fetch(1, w_nxt, b_nxt);
+  const unsigned kbytes = (unsigned)k * 8u;
   for (int t = 0; t < ntile; ++t) {
     fetch(t + 2, w_nx2, b_nx2);
     const int slot = t % nstage, n = t / nstage;
     bk_mbar_wait(bk_smem_u32(&s_full[slot]), (unsigned)(n & 1));
-    const double* tile = ring + slot * stage_doubles + (size_t)(warp * BK_RPW) * k;
-    const int64_t r0 = r_begin + (int64_t)t * BK_ROWS + warp * BK_RPW;
-    // branch-free over the warp's rows (rows past the end: weight 0 and the stale tile bytes are replaced by 0), in two
-    // groups of 4 so that the loads, dots and shuffles of independent rows interleave
+    const int64_t r0 = r_begin + (int64_t)t * BK_ROWS;
+    const int nr = (int)((r_end - r0) < BK_ROWS ? (r_end - r0) : BK_ROWS);     // rows of this tile that exist
+    const unsigned tile = bk_smem_u32(ring + slot * stage_doubles);
 #pragma unroll
-    for (int q0 = 0; q0 < BK_RPW; q0 += 4) {
-      double a[4][NPL], wv[4], bv[4], dot[4];
+    for (int it = 0; it < BK_RPW / 4; ++it) {
+      const int q = it * 4 + rs;                      // row of this warp's share of the tile
+      int row = warp * BK_RPW + q;
+      const double wv = __shfl_sync(0xffffffffu, w_cur, q);     // 0 for a test row and for rows past the end
+      const double bv = __shfl_sync(0xffffffffu, b_cur, q);
+      row = row < nr ? row : nr - 1;                  // ragged last tile: an existing row, weight 0
+      const unsigned raddr = tile + (unsigned)row * kbytes + (unsigned)cl * 16u;
+      double a0[NI], a1[NI];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        wv[q] = __shfl_sync(0xffffffffu, w_cur, q0 + q);
-        bv[q] = __shfl_sync(0xffffffffu, b_cur, q0 + q);
-        const bool valid = r0 + q0 + q < r_end;
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          const int c = lane + 32 * i;
-          const double v = (c < k) ? tile[(q0 + q) * k + c] : 0.0;
-          a[q][i] = valid ? v * wv[q] : 0.0;             // aw = w * a, rounded as the reference does (svd.py:44)
-        }
+      for (int i = 0; i < NI; ++i) {
+        double v0 = 0.0, v1 = 0.0;
+        if (2 * cl + 16 * i < k)
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(raddr + (unsigned)i * 128u));
+        a0[i] = v0 * wv;                              // aw = w * a, rounded as the reference does (svd.py:44)
+        a1[i] = v1 * wv;
       }
+      double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        dot[q] = 0.0;
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) dot[q] += a[q][i] * xr[i];
+      for (int i = 0; i < NI; ++i) {
+        d0 += a0[i] * x0[i];
+        d1 += a1[i] * x1[i];
       }
+      double dot = d0 + d1;
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+      const double res = wv * bv - dot;               // bw - aw x
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dot[q] += __shfl_xor_sync(0xffffffffu, dot[q], o);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const double res = wv[q] * bv[q] - dot[q];       // bw - aw x
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) gacc[i] += a[q][i] * res;
+      for (int i = 0; i < NI; ++i) {
+        g0[i] += a0[i] * res;
+        g1[i] += a1[i] * res;
       }
     }
     __syncwarp();
@@ -277,13 +285,22 @@ __global__ void __launch_bounds__(BK_THREADS, 1) rowpass_bulk_kernel(const doubl
     w_nxt = w_nx2; b_nxt = b_nx2;
   }
 
-  // fixed-order reduction over the consumer warps (the ring is free now: all tiles consumed by this warp,
-  // other warps may still read theirs -> use a separate region past the ring)
-  double* sg = ring + (size_t)nstage * stage_doubles;      // BK_NW x k doubles
+  // the four row groups of the warp, in a fixed order; then the consumer warps, in a fixed order (the ring is free
+  // now: all tiles consumed by this warp, other warps may still read theirs -> a separate region past the ring)
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    const int c = lane + 32 * i;
-    if (c < k) sg[warp * k + c] = gacc[i];
+  for (int i = 0; i < NI; ++i) {
+    g0[i] += __shfl_xor_sync(0xffffffffu, g0[i], 8);
+    g1[i] += __shfl_xor_sync(0xffffffffu, g1[i], 8);
+    g0[i] += __shfl_xor_sync(0xffffffffu, g0[i], 16);
+    g1[i] += __shfl_xor_sync(0xffffffffu, g1[i], 16);
+  }
+  double* sg = ring + (size_t)nstage * stage_doubles;      // BK_NW x k doubles
+  if (rs == 0) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int c = 2 * cl + 16 * i;
+      if (c < k) { sg[warp * k + c] = g0[i]; sg[warp * k + c + 1] = g1[i]; }
+    }
   }
   asm volatile("bar.sync 1, %0;" ::"n"(BK_CONSUMERS) : "memory");
   for (int c = tid; c < k; c += BK_CONSUMERS) {
@@ -427,18 +444,25 @@ int launch_rowpass_bulk(const fsb_context* h, const double* A, const double* b, 
   const size_t smem = (size_t)nstage * stage + tail;
   const int grid = h->sm_count;
   const int64_t rows_per_cta = fsb_round_up(fsb_ceil_div(n_rows, grid), BK_ROWS);
-  const int npl = (k + 31) / 32;
-#define FSB_BULK(NPL)                                                                                          \
+  const int ni = (k + 15) / 16;
+#define FSB_BULK(NI)                                                                                           \
   do {                                                                                                         \
-    FSB_CUDA_TRY(cudaFuncSetAttribute(rowpass_bulk_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+    FSB_CUDA_TRY(cudaFuncSetAttribute(rowpass_bulk_kernel<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                       (int)smem));                                                             \
-    rowpass_bulk_kernel<NPL><<<grid, BK_THREADS, smem, s>>>(A, b, w, testing, n_rows, k, x, out, rows_per_cta, \
-                                                            nstage);                                           \
+    rowpass_bulk_kernel<NI><<<grid, BK_THREADS, smem, s>>>(A, b, w, testing, n_rows, k, x, out, rows_per_cta,  \
+                                                           nstage);                                            \
   } while (0)
-  if (npl <= 1) FSB_BULK(1);
-  else if (npl <= 2) FSB_BULK(2);
-  else if (npl <= 4) FSB_BULK(4);
-  else return FSB_ERR_UNSUPPORTED;   // rowpass_bulk_ok admits k <= 128 only
+  switch (ni) {
+    case 1: FSB_BULK(1); break;
+    case 2: FSB_BULK(2); break;
+    case 3: FSB_BULK(3); break;
+    case 4: FSB_BULK(4); break;
+    case 5: FSB_BULK(5); break;
+    case 6: FSB_BULK(6); break;
+    case 7: FSB_BULK(7); break;
+    case 8: FSB_BULK(8); break;
+    default: return FSB_ERR_UNSUPPORTED;   // rowpass_bulk_ok admits k <= 128 only
+  }
 #undef FSB_BULK
   FSB_LAUNCH_CHECK("rowpass_bulk_kernel");
   *nparts = grid;

@@ -77,13 +77,9 @@ class HostStager:
         self.slots = [torch.empty(self.SLOT_BYTES, dtype=torch.uint8).pin_memory() for _ in range(self.NSLOT)]
         self.events = [None] * self.NSLOT
         self.next = 0
-        # the fill (pageable -> pinned memcpy) is the slow half of the pipeline (34 GB/s with 8 threads on a 16-core
-        # host against 55 GB/s of PCIe): use the cores this process may run on, less two for Python and the driver
-        try:
-            ncpu = len(os.sched_getaffinity(0))
-        except (AttributeError, OSError):
-            ncpu = os.cpu_count() or 2
-        nthr = max(1, min(16, ncpu - 2))
+        # 8 copy threads: measured on the 16-core bench host, 14 threads LOWER the upload rate of a pageable 816 MB
+        # matrix from 34 to 28 GB/s (they compete with the DMA reads of the pinned slots for memory bandwidth)
+        nthr = max(1, min(8, (os.cpu_count() or 2) // 2))
         self.pool = ThreadPoolExecutor(max_workers=nthr)
         self.nthr = nthr
 
