@@ -296,6 +296,7 @@ struct FusedArgs {
   double* partial;
   const struct FusedDesc* desc;   // per-row descriptors (row_resolve_kernel)
   int store_a;              // 0: streaming mode, A is not materialised (b and w still are)
+  int spec_from_a;          // 1: the energy / virial rows of A were written by special_rows_kernel before this launch
 };
 
 struct FusedDesc {           // one per output row, written by row_resolve_kernel
@@ -346,6 +347,41 @@ __global__ void __launch_bounds__(256) row_resolve_kernel(ScatterArgs a, const u
   a.w[row0 + i] = wv;
   d.wg = (testing && __ldg(testing + i)) ? 0.0 : wv;
   desc[i] = d;
+}
+
+// Energy and virial rows of A (7 of the rows of a configuration), computed BEFORE the fused kernel: one CTA per row,
+// one thread per column, the arithmetic of scatter_kernel (same operations, same order: bit-identical values).
+// Why not inside scatter_gram_kernel: an fp64 division is ~10 dependent fp64 operations, and every fp64 operation of
+// a producer warp queues behind the consumers' DMMAs on the shared fp64 pipe.  Measured on 1e6 x 100 (7 % special
+// rows): those rows took ~46 % of the producers' busy time, the producers -- not the DMMA pipe -- set the pace of the
+// kernel (consumers 27 % of their time at the FULL barrier), and the kernel time grew LINEARLY with the number of fp64
+// operations the producers issue per stage (0.61 ms at ~27, 0.70 ms at ~40, 0.83 ms at ~96: interleaving independent
+// division chains did not help, the pipe serialises them).  With this kernel the producers issue no fp64 operation
+// at all for these rows: they copy the finished values from A (L2-resident, written microseconds earlier) into the
+// DMMA ring.
+__global__ void __launch_bounds__(128) special_rows_kernel(ScatterArgs a) {
+  const int cfg = blockIdx.x / 7, sub = blockIdx.x - 7 * cfg;      // sub 0: energy row, 1..6: virial rows
+  const bool bzero = a.flags & FSB_BZEROFLAG, do_scrub = a.flags & FSB_SCRUB_NONFINITE;
+  const int kraw = a.ncoeff * a.numtypes;
+  const int k = bzero ? kraw : kraw + a.numtypes;
+  const int col = threadIdx.x;
+  if (col >= k) return;
+  const int n = __ldg(a.natoms + cfg);
+  const int64_t local = (sub == 0) ? 0 : 3 * (int64_t)n + sub;     // row inside the configuration (raw and output)
+  const int64_t orow = __ldg(a.out_row_off + cfg) + local;
+  const int64_t rrow = __ldg(a.raw_row_off + cfg) + local;
+  int srcc = col;
+  if (!bzero) {
+    const int seg = a.ncoeff + 1;
+    const int t = col / seg, q = col - t * seg;
+    srcc = (q == 0) ? -(t + 1) : t * a.ncoeff + q - 1;
+  }
+  double x = (srcc >= 0) ? __ldg(a.raw + rrow * (int64_t)(kraw + 1) + srcc) : 0.0;
+  if (do_scrub) { bool dummy = false; x = fsb_dev::scrub(x, true, dummy); }
+  double val;
+  if (sub == 0) val = (srcc >= 0) ? x / (double)n : __ldg(a.type_fraction + (size_t)cfg * a.numtypes + (-srcc - 1));
+  else val = (srcc >= 0) ? (FSB_VIRIAL_UNIT * x) / __ldg(a.volume + cfg) : 0.0;       // lammps_snap.py:526-536
+  a.A[orow * a.lda + col] = val * __ldg(a.blank2j + col);
 }
 
 // value of A for an energy / virial row (or any row when non-finite raw values are being scrubbed): out of line, the two
@@ -493,6 +529,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p,
       load_desc(s + 1, dB);
       const unsigned valid = __ballot_sync(0xffffffffu, dA.kind >= 0);
       const unsigned special = __ballot_sync(0xffffffffu, dA.kind == 0 || dA.kind == 2);
+      const unsigned spec_mask = p.spec_from_a ? special : 0u;       // rows of A that are final already: not stored here
       const int rslot = s % FZ_RAW_STAGES;
       double* rtile = raw_ring + (size_t)rslot * raw_stage;
       fz_mbar_wait(fz_smem_u32(&raw_full[rslot]), (unsigned)((s / FZ_RAW_STAGES) & 1));
@@ -532,7 +569,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p,
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               acc |= ((unsigned)__double2hiint(x[u]) & 0x7ff00000u) + 0x00100000u;
-              if (do_store) arow[0] = x[u];                          // blank2J == 1: A = R
+              if (do_store && !((spec_mask >> (j0 + u)) & 1u)) arow[0] = x[u];   // blank2J == 1: A = R
               arow += a.lda;
               if (ring_thread) fz_sts(s_addr + (unsigned)((j0 + u) * PITCH * 8), x[u]);      // padding columns: x = 0
             }
@@ -551,7 +588,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p,
             for (int u = 0; u < 8; ++u) {
               acc |= ((unsigned)__double2hiint(x[u]) & 0x7ff00000u) + 0x00100000u;
               const double val = x[u] * pref;                        // lead columns hold x = 0
-              if (do_store) arow[0] = val;
+              if (do_store && !((spec_mask >> (j0 + u)) & 1u)) arow[0] = val;
               arow += a.lda;
               if (ring_thread) fz_sts(s_addr + (unsigned)((j0 + u) * PITCH * 8), val);
             }
@@ -565,7 +602,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p,
           const double x = (loads_raw && ok) ? rs[j * ldr] : 0.0;
           nf |= ((unsigned)__double2hiint(x) & 0x7ff00000u) == 0x7ff00000u ? (1u << j) : 0u;
           const double val = x * pref;
-          if (do_store && ok) arow[0] = val;
+          if (do_store && ok && !((spec_mask >> j) & 1u)) arow[0] = val;
           arow += a.lda;
           if (ring_thread) st[j * PITCH] = (acol && ok) ? val : 0.0;
         }
@@ -576,6 +613,22 @@ __global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p,
       if (do_scrub && __any_sync(0xffffffffu, nf != 0u)) redo = valid;           // numpy.nan_to_num: rare
       if (redo) {
         arow = a.A + (row0 + row_begin + (int64_t)s * S_RCH) * a.lda + c;
+        unsigned copy = redo & spec_mask;                        // finished by special_rows_kernel: A -> ring
+        redo &= ~spec_mask;
+        while (copy) {                                           // warp-uniform; 8 independent loads per batch
+          int jj[8];
+          double xv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            jj[u] = copy ? __ffs((int)copy) - 1 : -1;
+            copy &= copy - 1u;                                   // 0 stays 0
+            xv[u] = 0.0;
+            if (acol && jj[u] >= 0) xv[u] = arow[(int64_t)jj[u] * a.lda];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (acol && jj[u] >= 0) st[jj[u] * PITCH] = xv[u];
+        }
         while (redo) {                                           // warp-uniform: only the rows that need it
           const int j = __ffs((int)redo) - 1;
           redo &= redo - 1u;
@@ -696,6 +749,13 @@ int fsb_launch_scatter_gram_small(const fsb_context* h, const ScatterArgs& sc, c
   a.desc = (const FusedDesc*)desc;
   row_resolve_kernel<<<(unsigned)fsb_ceil_div(total, 256), 256, 0, s>>>(sc, testing, total, (FusedDesc*)desc);
   FSB_LAUNCH_CHECK("row_resolve_kernel");
+  static int no_pre = -1;          // development switch: the divisions of the special rows inside the fused kernel
+  if (no_pre < 0) no_pre = getenv("FSB_FUSED_NO_PRESPECIAL") ? 1 : 0;
+  a.spec_from_a = (store_a && sc.A && sc.ncfg > 0 && !no_pre) ? 1 : 0;
+  if (a.spec_from_a) {
+    special_rows_kernel<<<(unsigned)(7 * sc.ncfg), 128, 0, s>>>(sc);
+    FSB_LAUNCH_CHECK("special_rows_kernel");
+  }
   const int want = fsb_gram_small_ctas(h, total);
   a.rows_per_cta = fsb_round_up(fsb_ceil_div(total > 0 ? total : 1, want), S_RCH);
   switch (nb) {

@@ -113,4 +113,5 @@ def test_pipeline_uses_the_fused_kernel_and_matches_the_unfused_fit(engine):
     plain = pipe.fit_batch(batch)
     n_plain = engine.launch_count - n0
     assert torch.equal(fused.x, plain.x) and torch.equal(fused.gaug, plain.gaug)
-    assert n_fused <= n_plain                          # row resolve + fused kernel + reduction vs scatter + Gram + reduction
+    # row resolve + special rows + fused kernel + reduction  vs  scatter + Gram + reduction
+    assert n_fused <= n_plain + 1
