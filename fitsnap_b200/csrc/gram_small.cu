@@ -653,6 +653,17 @@ __global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p,
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fz_smem_u32(&raw_empty[rslot])) : "memory");
       __threadfence_block();
       bar_arrive(1 + (s % nstage_d), S_THREADS);                               // FULL[slot] of the DMMA ring
+      if (p.spec_from_a) {
+        // the finished energy / virial rows of the NEXT stage: pull them towards this SM now (they were written by
+        // special_rows_kernel and have usually left L2 again), so that the copy loop above does not wait on DRAM
+        unsigned nxt = __ballot_sync(0xffffffffu, dB.kind == 0 || dB.kind == 2);
+        const double* nrow = a.A + (row0 + row_begin + (int64_t)(s + 1) * S_RCH) * a.lda + c;
+        while (nxt) {
+          const int j = __ffs((int)nxt) - 1;
+          nxt &= nxt - 1u;
+          if (acol) asm volatile("prefetch.global.L1 [%0];" ::"l"(nrow + (int64_t)j * a.lda));
+        }
+      }
       dA = dB;
     }
     if (a.nonfinite && __any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(a.nonfinite, 1);

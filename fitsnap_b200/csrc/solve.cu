@@ -146,95 +146,94 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(FactorView f, int p, do
   }
 }
 
-// Cholesky of the 64x64 diagonal block of panel p AND its inverse, one CTA, compact loops.
+// Cholesky of the 64x64 diagonal block of panel p AND its inverse, one CTA of 16 x 16 threads, compact loops.
 // (The first version -- potrf_diag_kernel above, right-looking with three block barriers per column, followed by
 // trsm_panel_kernel / trtri_diag_kernel whose fully unrolled 64-step substitutions run ONCE per launch -- spent
 // 64 + 42 us per panel at k = 1000 (profiles/r02_launches_bench_default.csv): barrier latency in the first,
-// instruction-cache misses on ~6000 straight-line instructions in the other two.)
-//   factor : left-looking.  Thread (r, q), q = tid % 4: the dot of rows r and j over the columns c < j, c = q mod 4,
-//            and the same for the pivot (row j with itself, a broadcast read); two shuffle levels combine the four
-//            parts.  New diagonal entries go to their own array, so ONE block barrier per column suffices.
-//   inverse: X = L^-1 row by row: X[r][j] = -(1 / L[r][r]) sum_{c = j}^{r-1} L[r][c] X[c][j], all 64 columns at once
-//            (thread (j, q) takes the c = q mod 4 part).  Written to the diagonal block of f.Linv: the panel solve
-//            becomes a 64x64x64 product (trsm_gemm_kernel) and trtri_diag_kernel is not needed any more.
+// instruction-cache misses on ~6000 straight-line instructions in the other two.  A left-looking version with one
+// barrier per column but a 16-slot dot product per thread and step took 76 us: ~220 instructions per step.)
+// Both phases are right-looking in "unscaled" form, so that a step is: read the pivot, ONE reciprocal, a rank-1 update
+// of at most 4 x 4 elements per thread, ONE block barrier -- no column / row scaling inside the loops:
+//   factor : column j of S keeps the values it has when pivot p_j is reached (= L[r][j] sqrt(p_j));
+//            S[r][c] -= S[r][j] S[c][j] / p_j for j < c <= r.  ip[j] = 1 / p_j, or 0 for a dropped column.
+//   inverse: Y = I; row r of Y is final (up to the factor 1 / L[r][r]) when step r is reached;
+//            Y[r2][c] -= (S[r2][r] / p_r) Y[r][c] for r2 > r, c <= r   (L[r2][r] / L[r][r] = S[r2][r] / p_r).
+//   after the loops: L[r][c] = S[r][c] / sqrt(p_c), X[r][c] = Y[r][c] / sqrt(p_r).
+// X goes to the diagonal block of f.Linv: the panel solve becomes a 64x64x64 product (trsm_gemm_kernel) and
+// trtri_diag_kernel is not needed any more.
 __global__ void __launch_bounds__(256) potrf_inv_kernel(FactorView f, int p, double tol, int32_t* info) {
-  extern __shared__ double pi_sm[];             // s[NB][NBP] | xinv[NB][NBP]: 66.6 KB, dynamic (above the static limit)
+  extern __shared__ double pi_sm[];             // s[NB][NBP] | y[NB][NBP]: 66.6 KB, dynamic (above the static limit)
   double (*s)[NBP] = reinterpret_cast<double (*)[NBP]>(pi_sm);
-  double (*xinv)[NBP] = reinterpret_cast<double (*)[NBP]>(pi_sm + NB * NBP);
-  __shared__ double diag[NB], rdiag[NB];
-  __shared__ int dropped[NB];
+  double (*y)[NBP] = reinterpret_cast<double (*)[NBP]>(pi_sm + NB * NBP);
+  __shared__ double pivv[NB], ipv[NB];          // pivot (0: dropped), reciprocal pivot (0: dropped)
   const int kp = f.kp, tid = threadIdx.x;
   double* blk = f.L + (size_t)(p * NB) * kp + p * NB;
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int r = idx / NB, c = idx % NB;
     s[r][c] = (c <= r) ? blk[(size_t)r * kp + c] : 0.0;
-    xinv[r][c] = 0.0;
+    y[r][c] = (c == r) ? 1.0 : 0.0;
   }
   __syncthreads();
-  const int r = tid >> 2, q = tid & 3;
+  const int ty = tid >> 4, tx = tid & 15;
   // diag(S) lies in [0.5, 2) after equilibration, so `tol` is an absolute pivot threshold.
-  // The dots run over a FIXED 16 slots per thread (column q + 4 i, predicated on < j): all shared-memory loads of a
-  // step are issued back to back instead of one dependent load -> multiply-add pair per iteration.
   for (int j = 0; j < NB; ++j) {
-    double lj[NB / 4], lr[NB / 4];
+    const double pj = s[j][j];
+    const bool drop = !(pj > tol);
+    const double inv = drop ? 0.0 : 1.0 / pj;
+    if (tid == 0) { pivv[j] = drop ? 0.0 : pj; ipv[j] = inv; }
+    if (!drop) {
+      double cj[4];
 #pragma unroll
-    for (int i = 0; i < NB / 4; ++i) {
-      const int c = q + 4 * i;
-      lj[i] = (c < j) ? s[j][c] : 0.0;
-      lr[i] = (c < j) ? s[r][c] : 0.0;
-    }
-    double dr0 = 0.0, dr1 = 0.0, dp0 = 0.0, dp1 = 0.0;
+      for (int b2 = 0; b2 < 4; ++b2) cj[b2] = s[tx + 16 * b2][j];
 #pragma unroll
-    for (int i = 0; i < NB / 4; i += 2) {
-      dr0 += lr[i] * lj[i];
-      dp0 += lj[i] * lj[i];
-      dr1 += lr[i + 1] * lj[i + 1];
-      dp1 += lj[i + 1] * lj[i + 1];
-    }
-    double dr = dr0 + dr1, dp = dp0 + dp1;
-    dr += __shfl_xor_sync(0xffffffffu, dr, 1);
-    dp += __shfl_xor_sync(0xffffffffu, dp, 1);
-    dr += __shfl_xor_sync(0xffffffffu, dr, 2);
-    dp += __shfl_xor_sync(0xffffffffu, dp, 2);
-    const double piv = s[j][j] - dp;
-    const bool drop = !(piv > tol);
-    const double rl = drop ? 1.0 : rsqrt(piv);         // one reciprocal square root instead of sqrt + division
-    const double ljj = drop ? 1.0 : piv * rl;
-    if (q == 0) {
-      if (r > j) s[r][j] = drop ? 0.0 : (s[r][j] - dr) * rl;
-      if (r == j) { diag[j] = ljj; rdiag[j] = rl; dropped[j] = drop ? 1 : 0; }
+      for (int a = 0; a < 4; ++a) {
+        const int r = ty + 16 * a;
+        if (r > j) {
+          const double fr = s[r][j] * inv;
+#pragma unroll
+          for (int b2 = 0; b2 < 4; ++b2) {
+            const int c = tx + 16 * b2;
+            if (c > j && c <= r) s[r][c] -= fr * cj[b2];
+          }
+        }
+      }
     }
     __syncthreads();
   }
-  // inverse, row by row (row r of X needs rows j..r-1); same fixed-slot dots: c = jc + q + 4 i < rr
-  const int jc = tid >> 2;                       // column of X owned by this group of four lanes
-  for (int rr = 0; rr < NB; ++rr) {
-    double a0 = 0.0, a1 = 0.0;
-    double ls[NB / 4], xs[NB / 4];
+  for (int r = 0; r < NB; ++r) {
+    const double ipr = ipv[r];
+    if (ipr != 0.0) {
+      double yr[4];
 #pragma unroll
-    for (int i = 0; i < NB / 4; ++i) {
-      const int c = jc + q + 4 * i;
-      ls[i] = (c < rr) ? s[rr][c] : 0.0;
-      xs[i] = (c < rr) ? xinv[c][jc] : 0.0;
-    }
+      for (int b2 = 0; b2 < 4; ++b2) yr[b2] = y[r][tx + 16 * b2];
 #pragma unroll
-    for (int i = 0; i < NB / 4; i += 2) {
-      a0 += ls[i] * xs[i];
-      a1 += ls[i + 1] * xs[i + 1];
+      for (int a = 0; a < 4; ++a) {
+        const int r2 = ty + 16 * a;
+        if (r2 > r) {
+          const double fr = s[r2][r] * ipr;
+#pragma unroll
+          for (int b2 = 0; b2 < 4; ++b2) {
+            const int c = tx + 16 * b2;
+            if (c <= r) y[r2][c] -= fr * yr[b2];
+          }
+        }
+      }
     }
-    double acc = a0 + a1;
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    if (q == 0 && jc <= rr) xinv[rr][jc] = (jc == rr) ? rdiag[rr] : -rdiag[rr] * acc;
     __syncthreads();
   }
   double* out = f.Linv + (size_t)(p * NB) * f.kp2 + p * NB;
   for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int rr = idx / NB, c = idx % NB;
-    if (c <= rr) blk[(size_t)rr * kp + c] = (c == rr) ? diag[rr] : s[rr][c];
-    out[(size_t)rr * f.kp2 + c] = xinv[rr][c];
+    const int r = idx / NB, c = idx % NB;
+    const double pc = pivv[c], pr = pivv[r];
+    if (c <= r) {
+      double v;
+      if (pc == 0.0) v = (r == c) ? 1.0 : 0.0;                 // dropped column: e_c
+      else v = (r == c) ? sqrt(pc) : s[r][c] * rsqrt(pc);
+      blk[(size_t)r * kp + c] = v;
+    }
+    out[(size_t)r * f.kp2 + c] = (c <= r) ? y[r][c] * (pr == 0.0 ? 1.0 : rsqrt(pr)) : 0.0;
   }
-  if (tid < NB && dropped[tid]) {
+  if (tid < NB && pivv[tid] == 0.0) {
     const int col = p * NB + tid;
     f.flag[col] = 1.0;
     f.d[col] = 0.0;
@@ -492,12 +491,15 @@ __global__ void __launch_bounds__(512) small_factor_kernel(const double* __restr
   }
   __syncthreads();
 
-  // Blocked left-looking Cholesky, panels of PB columns.  (1) the panel is updated with all
-  // previous columns at once (every thread owns (row, panel column) elements and runs a dot product
-  // over the finished columns: no barrier inside), (2) the PB columns of the panel are factored one
-  // by one; only the panel is touched there, so those 2 barriers per column guard very little work.
-  // Columns are stored already scaled (true L); dropped columns are zeroed and flagged in piv[].
+  // Blocked left-looking Cholesky, panels of PB columns, in "unscaled column" form: column j of S keeps the values
+  // it has when its pivot p_j is reached (= L[r][j] sqrt(p_j)); every later use multiplies by 1 / p_j instead
+  // (S[r][c] -= S[r][j] S[c][j] / p_j).  No column-scaling pass inside the loop, hence ONE block barrier per column
+  // (round 1 scaled the column in place: three barriers and a sqrt + division chain per column, ~1 us each); the
+  // columns are scaled once, in parallel, after the loop.  ip[j] = 1 / p_j, or 0 for a dropped column (its
+  // contributions vanish).  (1) a new panel is updated with all finished columns at once (dot products over m < p0,
+  // no barrier inside), (2) its PB columns are eliminated one by one inside the panel.
   constexpr int PB = 16;
+  double* ip = dsc + k;                  // k   reciprocal pivots (shared-memory region sized by the launcher)
   for (int p0 = 0; p0 < k; p0 += PB) {
     const int pw = (k - p0) < PB ? (k - p0) : PB;
     if (p0 > 0) {
@@ -507,9 +509,14 @@ __global__ void __launch_bounds__(512) small_factor_kernel(const double* __restr
         if (c < p0 + pw && c <= r) {
           const double* sr = S + r * P;
           const double* sc = S + c * P;
-          double acc = 0.0;
-          for (int m = 0; m < p0; ++m) acc += sr[m] * sc[m];
-          S[r * P + c] -= acc;
+          double acc0 = 0.0, acc1 = 0.0;
+          int m = 0;
+          for (; m + 1 < p0; m += 2) {
+            acc0 += sr[m] * sc[m] * ip[m];
+            acc1 += sr[m + 1] * sc[m + 1] * ip[m + 1];
+          }
+          if (m < p0) acc0 += sr[m] * sc[m] * ip[m];
+          S[r * P + c] -= acc0 + acc1;
         }
       }
       __syncthreads();
@@ -517,25 +524,30 @@ __global__ void __launch_bounds__(512) small_factor_kernel(const double* __restr
     for (int j = p0; j < p0 + pw; ++j) {
       const double pj = S[j * P + j];
       const bool drop = !(pj > tol);
-      const double ljj = drop ? 1.0 : sqrt(pj);
-      const double inv = 1.0 / ljj;
-      __syncthreads();                       // everyone has read the pivot before it is overwritten
-      if (tid == 0) { piv[j] = drop ? 0.0 : pj; S[j * P + j] = ljj; }
-      for (int r = j + 1 + tid; r < k; r += nt) S[r * P + j] = drop ? 0.0 : S[r * P + j] * inv;
-      __syncthreads();
-      if (!drop) {
-        const int nc = p0 + pw - (j + 1);    // remaining panel columns
-        if (nc > 0) {
-          const int nel = (k - (j + 1)) * PB;
-          for (int idx = tid; idx < nel; idx += nt) {
-            const int r = j + 1 + (idx >> 4), c = j + 1 + (idx & (PB - 1));
-            if (c < p0 + pw && c <= r) S[r * P + c] -= S[r * P + j] * S[c * P + j];
-          }
+      const double inv = drop ? 0.0 : 1.0 / pj;
+      if (tid == 0) { piv[j] = drop ? 0.0 : pj; ip[j] = inv; }
+      const int nc = p0 + pw - (j + 1);      // remaining panel columns
+      if (nc > 0 && !drop) {
+        const int nel = (k - (j + 1)) * PB;
+        for (int idx = tid; idx < nel; idx += nt) {
+          const int r = j + 1 + (idx >> 4), c = j + 1 + (idx & (PB - 1));
+          if (c < p0 + pw && c <= r) S[r * P + c] -= S[r * P + j] * (S[c * P + j] * inv);
         }
       }
       __syncthreads();
     }
   }
+  // scale: L[r][j] = S[r][j] / sqrt(p_j); dropped columns become (1 on the diagonal, 0 below)
+  for (int idx = tid; idx < k * k; idx += nt) {
+    const int r = idx / k, c = idx - r * k;
+    if (c > r) continue;
+    const double pc = piv[c];
+    double v;
+    if (pc == 0.0) v = (r == c) ? 1.0 : 0.0;
+    else v = (r == c) ? sqrt(pc) : S[r * P + c] * rsqrt(pc);
+    S[r * P + c] = v;
+  }
+  __syncthreads();
 
   // scale the columns, publish the factor in the common layout (pitch kp, identity padding)
   if (tid < FSB_INFO_LEN) info[tid] = (tid == FSB_INFO_FIRST_BAD_COLUMN) ? k : 0;
@@ -854,7 +866,7 @@ int fsb_launch_factor(const fsb_context* h, const double* gaug, int k, double al
   FactorView f = view_factor(factor, k);
   if (k <= SMALL_K) {
     const int P = k | 1;
-    const size_t smem = ((size_t)k * P + 2 * (size_t)k) * sizeof(double);
+    const size_t smem = ((size_t)k * P + 3 * (size_t)k) * sizeof(double);
     FSB_CUDA_TRY(cudaFuncSetAttribute(small_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     small_factor_kernel<<<1, 512, smem, s>>>(gaug, k, alpha, f, 64.0 * (double)f.kp * DBL_EPSILON, info);
     FSB_LAUNCH_CHECK("small_factor_kernel");
