@@ -668,6 +668,18 @@ EncodeTiledFn get_encode() {
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+int converter_threads() {             // development switch: FSB_I8_CONVERTERS = 0 (default) | 256 | 512
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FSB_I8_CONVERTERS");
+    v = e ? atoi(e) : 0;
+    if (v < 0) v = 0;
+    v = (v / CV_THREADS) * CV_THREADS;
+    if (v > 32 * NCW) v = 32 * NCW;
+  }
+  return v;
+}
+
 struct I8Plan {
   int ka, n_i, ntile, kp, kpc, ka_pad, nbuf;
   int64_t slab_rows, nslab;
@@ -686,7 +698,7 @@ I8Plan plan_i8(int64_t n_rows, int k) {
   const int64_t n = n_rows > 0 ? n_rows : 1;
   pl.nslab = fsb_ceil_div(n, SLAB_ROWS);
   pl.slab_rows = fsb_round_up(fsb_ceil_div(n, pl.nslab), CV_ROWS);
-  pl.nbuf = pl.nslab > 1 ? 2 : 1;      // slab s+1 is converted while slab s is contracted
+  pl.nbuf = (pl.nslab > 1 && converter_threads() > 0) ? 2 : 1;   // a second plane buffer only when slab s+1 is converted beside the contraction of slab s
   pl.off_colmax = 0;
   pl.off_flag = align256((size_t)pl.nslab * pl.ka_pad * sizeof(unsigned long long));
   pl.off_table = pl.off_flag + 256;
@@ -695,18 +707,6 @@ I8Plan plan_i8(int64_t n_rows, int k) {
   pl.plane_bytes = ((size_t)NMOD * pl.kpc * (size_t)pl.slab_rows + 1023) & ~(size_t)1023;
   pl.total = pl.off_planes + pl.nbuf * pl.plane_bytes + 1024;   // + slack to align the base
   return pl;
-}
-
-int converter_threads() {             // development switch: FSB_I8_CONVERTERS = 0 (default) | 256 | 512
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("FSB_I8_CONVERTERS");
-    v = e ? atoi(e) : 0;
-    if (v < 0) v = 0;
-    v = (v / CV_THREADS) * CV_THREADS;
-    if (v > 32 * NCW) v = 32 * NCW;
-  }
-  return v;
 }
 
 }  // namespace
