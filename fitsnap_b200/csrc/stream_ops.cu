@@ -223,32 +223,37 @@ __global__ void __launch_bounds__(BK_THREADS, 1) rowpass_bulk_kernel(const doubl
     x1[i] = (c < k) ? x[c + 1] : 0.0;
     g0[i] = 0.0; g1[i] = 0.0;
   }
-  // lane q < BK_RPW keeps (w, b) of row BK_RPW * warp + q of the tile; test rows and rows past the end get w = 0
-  auto fetch = [&](int t, double& wv, double& bv) {
-    wv = 0.0; bv = 0.0;
+  // lane q < BK_RPW keeps (w, b, test flag) of row BK_RPW * warp + q of the tile, loaded TWO tiles ahead and not
+  // touched until that tile is current: the first version selected w = 0 for test rows right behind the loads, which
+  // made every fetch wait for its own DRAM round trip (33 % of the kernel's stall samples on that one FSEL,
+  // profiles/r02b_rowpass_c2.txt).  Rows past the end keep w = 0.
+  auto fetch = [&](int t, double& wv, double& bv, unsigned& tv) {
+    wv = 0.0; bv = 0.0; tv = 0u;
     const int64_t r = r_begin + (int64_t)t * BK_ROWS + warp * BK_RPW + (lane & (BK_RPW - 1));
     if (t < ntile && r < r_end) {
       bv = __ldg(b + r);
-      const double ww = __ldg(w + r);
-      wv = (testing && __ldg(testing + r)) ? 0.0 : ww;
+      wv = __ldg(w + r);
+      if (testing) tv = (unsigned)__ldg(testing + r);
     }
   };
   double w_cur, b_cur, w_nxt, b_nxt, w_nx2, b_nx2;
-  fetch(0, w_cur, b_cur);
-  fetch(1, w_nxt, b_nxt);
+  unsigned t_cur, t_nxt, t_nx2;
+  fetch(0, w_cur, b_cur, t_cur);
+  fetch(1, w_nxt, b_nxt, t_nxt);
   const unsigned kbytes = (unsigned)k * 8u;
   for (int t = 0; t < ntile; ++t) {
-    fetch(t + 2, w_nx2, b_nx2);
+    fetch(t + 2, w_nx2, b_nx2, t_nx2);
     const int slot = t % nstage, n = t / nstage;
     bk_mbar_wait(bk_smem_u32(&s_full[slot]), (unsigned)(n & 1));
     const int64_t r0 = r_begin + (int64_t)t * BK_ROWS;
     const int nr = (int)((r_end - r0) < BK_ROWS ? (r_end - r0) : BK_ROWS);     // rows of this tile that exist
     const unsigned tile = bk_smem_u32(ring + slot * stage_doubles);
+    const double w_use = t_cur ? 0.0 : w_cur;        // test rows: weight 0 (selected now, two tiles after the loads)
 #pragma unroll
     for (int it = 0; it < BK_RPW / 4; ++it) {
       const int q = it * 4 + rs;                      // row of this warp's share of the tile
       int row = warp * BK_RPW + q;
-      const double wv = __shfl_sync(0xffffffffu, w_cur, q);     // 0 for a test row and for rows past the end
+      const double wv = __shfl_sync(0xffffffffu, w_use, q);     // 0 for a test row and for rows past the end
       const double bv = __shfl_sync(0xffffffffu, b_cur, q);
       row = row < nr ? row : nr - 1;                  // ragged last tile: an existing row, weight 0
       const unsigned raddr = tile + (unsigned)row * kbytes + (unsigned)cl * 16u;
@@ -281,8 +286,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) rowpass_bulk_kernel(const doubl
     __syncwarp();
     if (lane == 0)
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bk_smem_u32(&s_empty[slot])) : "memory");
-    w_cur = w_nxt; b_cur = b_nxt;
-    w_nxt = w_nx2; b_nxt = b_nx2;
+    w_cur = w_nxt; b_cur = b_nxt; t_cur = t_nxt;
+    w_nxt = w_nx2; b_nxt = b_nx2; t_nxt = t_nx2;
   }
 
   // the four row groups of the warp, in a fixed order; then the consumer warps, in a fixed order (the ring is free
