@@ -137,27 +137,32 @@ class LinearFitPipeline:
         kraw = self.ncoeff * self.numtypes
         raw = np.ascontiguousarray(raw, dtype=np.float64)
         assert raw.shape == (int(raw_off[-1]), kraw + 1), (raw.shape, int(raw_off[-1]), kraw + 1)
-        # The copy engine must never idle: the per-configuration scalars of ALL chunks (1 % of the bytes) go up first,
-        # in one go, then the raw chunks follow back to back into one device buffer -- round 2 measured 17.5 ms per
+        # The copy engine must never idle: the first raw chunk goes on the wire at once, the per-configuration scalars of
+        # ALL chunks (1 % of the bytes) follow in one go, then the other raw chunks back to back into one device buffer -- round 2 measured 17.5 ms per
         # step against 14.4 ms of pure PCIe time when every chunk re-uploaded its own 13 small arrays in between.
         with torch.cuda.stream(copy_stream):
             up = eng.to_device
+            raw_dev = torch.empty((int(raw_off[-1]), kraw + 1), dtype=torch.float64, device=dev)
+            chunk_events = []
+
+            def send_chunk(c0, c1):
+                r0, r1 = int(raw_off[int(c0)]), int(raw_off[int(c1)])
+                eng.upload_into(raw_dev[r0:r1], raw[r0:r1])
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                chunk_events.append(ev)
+
+            send_chunk(cuts[0], cuts[1])              # the wire is busy while the host prepares the small arrays
             meta = dict(volume=up(f64(volumes)), energy=up(f64(energies)), forces=up(forces), stress=up(stresses),
                         eweight=up(f64(eweights)), fweight=up(f64(fweights)), vweight=up(f64(vweights)),
                         type_fraction=up(tf), blank2j=up(self.blank2j))
             raw_off_dev = up(raw_off.astype(np.int64), dtype=torch.int64)
             out_off_dev = up(out_off.astype(np.int64), dtype=torch.int64)
             natoms_dev = up(natoms, dtype=torch.int32)
-            raw_dev = torch.empty((int(raw_off[-1]), kraw + 1), dtype=torch.float64, device=dev)
             ev_meta = torch.cuda.Event()
             ev_meta.record(copy_stream)
-            chunk_events = []
-            for c0, c1 in zip(cuts[:-1], cuts[1:]):
-                r0, r1 = int(raw_off[int(c0)]), int(raw_off[int(c1)])
-                eng.upload_into(raw_dev[r0:r1], raw[r0:r1])
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-                chunk_events.append(ev)
+            for c0, c1 in zip(cuts[1:-1], cuts[2:]):
+                send_chunk(c0, c1)
         h2d = raw.nbytes + sum(int(t.numel()) * t.element_size() for t in meta.values()) + \
             raw_off_dev.numel() * 8 + out_off_dev.numel() * 8 + natoms_dev.numel() * 4
         main.wait_event(ev_meta)
