@@ -514,7 +514,7 @@ def run_workload(eng, name, rank, world, group, steps, warmup, full, args, peaks
         pass
     if gram_path == "int8":
         n_i = -(-(k + 1) // 128)
-        ops = sum(2.0 * 128 * (256 if 2 * jj + 1 < n_i else 128) * n_rows * 16
+        ops = sum(2.0 * 128 * (256 if (2 * jj + 1 < n_i and 2 * jj + 1 <= i_) else 128) * n_rows * 16
                   for i_ in range(n_i) for jj in range(i_ // 2 + 1))
         top = ops / (gram_ms * 1e-3) / 1e12
         roofline.update({
