@@ -591,10 +591,13 @@ __global__ void __launch_bounds__(128) i8_crt_kernel(long long* __restrict__ tab
   const int i = j + blockIdx.x * 128 + threadIdx.x;
   if (i >= ka) return;
   int res[NMOD];
+  long long tv[NMOD];
+#pragma unroll
+  for (int t = 0; t < NMOD; ++t) tv[t] = __ldcg(table + ((size_t)t * kp + j) * kp + i);   // 16 loads in flight per thread
 #pragma unroll
   for (int t = 0; t < NMOD; ++t) {
     long long* cell = table + ((size_t)t * kp + j) * kp + i;
-    const long long v = *cell;
+    const long long v = tv[t];
     *cell = 0;                                   // ready for the next slab
     // |v| <= 4 units x 2^30: quotient estimate in fp64, then one correction step either way
     const int p = c_tab.mod[t];
