@@ -748,7 +748,9 @@ int fsb_launch_gram_i8(const fsb_context* h, const double* A, int64_t lda, const
   FSB_CUDA_TRY(cudaMemsetAsync(colmax, 0, (size_t)nslab * pl.ka_pad * sizeof(unsigned long long), s));
   {
     const int64_t nr = n_rows < pl.slab_rows ? n_rows : pl.slab_rows;
-    int64_t rb = fsb_ceil_div(nr, fsb_ceil_div((int64_t)h->sm_count * 8, fsb_ceil_div(ka, 256) * nslab));
+    // ~32 CTAs per SM in total: with exactly one resident wave + a few CTAs (1200 on 1184 slots at 5 slabs) the
+    // stragglers ran alone and the launch took 2.5 ms instead of 1.6 (profiles/r02_launches_bench_default.csv)
+    int64_t rb = fsb_ceil_div(nr, fsb_ceil_div((int64_t)h->sm_count * 32, fsb_ceil_div(ka, 256) * nslab));
     rb = fsb_round_up(rb < 64 ? 64 : rb, 8);
     dim3 grid((unsigned)fsb_ceil_div(ka, 256), (unsigned)fsb_ceil_div(nr, rb), (unsigned)nslab);
     i8_colmax_kernel<<<grid, 256, 0, s>>>(A, lda, b, weff, n_rows, k, pl.slab_rows, rb, colmax, pl.ka_pad, flag);

@@ -349,8 +349,8 @@ __global__ void __launch_bounds__(256) row_resolve_kernel(ScatterArgs a, const u
   desc[i] = d;
 }
 
-// Energy and virial rows of A (7 of the rows of a configuration), computed BEFORE the fused kernel: one CTA per row,
-// one thread per column, the arithmetic of scatter_kernel (same operations, same order: bit-identical values).
+// Energy and virial rows of A (7 of the rows of a configuration), computed BEFORE the fused kernel: one CTA per
+// configuration, the arithmetic of scatter_kernel (same operations, same order: bit-identical values).
 // Why not inside scatter_gram_kernel: an fp64 division is ~10 dependent fp64 operations, and every fp64 operation of
 // a producer warp queues behind the consumers' DMMAs on the shared fp64 pipe.  Measured on 1e6 x 100 (7 % special
 // rows): those rows took ~46 % of the producers' busy time, the producers -- not the DMMA pipe -- set the pace of the
@@ -359,29 +359,47 @@ __global__ void __launch_bounds__(256) row_resolve_kernel(ScatterArgs a, const u
 // division chains did not help, the pipe serialises them).  With this kernel the producers issue no fp64 operation
 // at all for these rows: they copy the finished values from A (L2-resident, written microseconds earlier) into the
 // DMMA ring.
-__global__ void __launch_bounds__(128) special_rows_kernel(ScatterArgs a) {
-  const int cfg = blockIdx.x / 7, sub = blockIdx.x - 7 * cfg;      // sub 0: energy row, 1..6: virial rows
+__global__ void __launch_bounds__(256) special_rows_kernel(ScatterArgs a) {
+  // one CTA per configuration: its 7 special rows x k columns are dealt to the 256 threads (<= 3 elements each for
+  // k <= 104), the per-configuration scalars are loaded once and every thread's raw loads are issued together -- with
+  // one 128-thread CTA per ROW the kernel was a chain of dependent loads over 70 000 tiny CTAs (60 us at 1e4
+  // configurations, a tenth of the fused phase)
+  const int cfg = blockIdx.x;
   const bool bzero = a.flags & FSB_BZEROFLAG, do_scrub = a.flags & FSB_SCRUB_NONFINITE;
   const int kraw = a.ncoeff * a.numtypes;
   const int k = bzero ? kraw : kraw + a.numtypes;
-  const int col = threadIdx.x;
-  if (col >= k) return;
+  const int seg = a.ncoeff + 1;
   const int n = __ldg(a.natoms + cfg);
-  const int64_t local = (sub == 0) ? 0 : 3 * (int64_t)n + sub;     // row inside the configuration (raw and output)
-  const int64_t orow = __ldg(a.out_row_off + cfg) + local;
-  const int64_t rrow = __ldg(a.raw_row_off + cfg) + local;
-  int srcc = col;
-  if (!bzero) {
-    const int seg = a.ncoeff + 1;
-    const int t = col / seg, q = col - t * seg;
-    srcc = (q == 0) ? -(t + 1) : t * a.ncoeff + q - 1;
+  const int64_t o0 = __ldg(a.out_row_off + cfg), r0 = __ldg(a.raw_row_off + cfg);
+  const double vol = __ldg(a.volume + cfg), dn = (double)n;
+  constexpr int EPT = 3;                                   // elements per thread: 7 * 104 <= 3 * 256
+  int sub[EPT], col[EPT], srcc[EPT];
+  double x[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int idx = threadIdx.x + 256 * e;
+    sub[e] = idx / k;                                      // 0: energy row, 1..6: virial rows; >= 7: nothing
+    col[e] = idx - sub[e] * k;
+    int v = col[e];
+    if (!bzero) {
+      const int t = col[e] / seg, q = col[e] - t * seg;
+      v = (q == 0) ? -(t + 1) : t * a.ncoeff + q - 1;
+    }
+    srcc[e] = v;
+    const int64_t local = (sub[e] == 0) ? 0 : 3 * (int64_t)n + sub[e];   // row inside the configuration (raw and output)
+    x[e] = (sub[e] < 7 && v >= 0) ? __ldg(a.raw + (r0 + local) * (int64_t)(kraw + 1) + v) : 0.0;
   }
-  double x = (srcc >= 0) ? __ldg(a.raw + rrow * (int64_t)(kraw + 1) + srcc) : 0.0;
-  if (do_scrub) { bool dummy = false; x = fsb_dev::scrub(x, true, dummy); }
-  double val;
-  if (sub == 0) val = (srcc >= 0) ? x / (double)n : __ldg(a.type_fraction + (size_t)cfg * a.numtypes + (-srcc - 1));
-  else val = (srcc >= 0) ? (FSB_VIRIAL_UNIT * x) / __ldg(a.volume + cfg) : 0.0;       // lammps_snap.py:526-536
-  a.A[orow * a.lda + col] = val * __ldg(a.blank2j + col);
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    if (sub[e] >= 7) continue;
+    double xv = x[e];
+    if (do_scrub) { bool dummy = false; xv = fsb_dev::scrub(xv, true, dummy); }
+    double val;
+    if (sub[e] == 0) val = (srcc[e] >= 0) ? xv / dn : __ldg(a.type_fraction + (size_t)cfg * a.numtypes + (-srcc[e] - 1));
+    else val = (srcc[e] >= 0) ? (FSB_VIRIAL_UNIT * xv) / vol : 0.0;                 // lammps_snap.py:526-536
+    const int64_t local = (sub[e] == 0) ? 0 : 3 * (int64_t)n + sub[e];
+    a.A[(o0 + local) * a.lda + col[e]] = val * __ldg(a.blank2j + col[e]);
+  }
 }
 
 // value of A for an energy / virial row (or any row when non-finite raw values are being scrubbed): out of line, the two
@@ -764,7 +782,7 @@ int fsb_launch_scatter_gram_small(const fsb_context* h, const ScatterArgs& sc, c
   if (no_pre < 0) no_pre = getenv("FSB_FUSED_NO_PRESPECIAL") ? 1 : 0;
   a.spec_from_a = (store_a && sc.A && sc.ncfg > 0 && !no_pre) ? 1 : 0;
   if (a.spec_from_a) {
-    special_rows_kernel<<<(unsigned)(7 * sc.ncfg), 128, 0, s>>>(sc);
+    special_rows_kernel<<<(unsigned)sc.ncfg, 256, 0, s>>>(sc);
     FSB_LAUNCH_CHECK("special_rows_kernel");
   }
   const int want = fsb_gram_small_ctas(h, total);
