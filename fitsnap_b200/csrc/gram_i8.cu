@@ -5,7 +5,8 @@
 // tensor cores can do (Ozaki scheme II: Chinese remainder theorem instead of mantissa slices):
 //
 //   per slab of <= 2^18 rows
-//   1. i8_colmax_kernel   m_c = max_r |fl(w_r a_rc)|  (augmented column c = k holds w_r b_r).  One HBM pass.
+//   1. i8_colmax_kernel   m_c = max_r |fl(w_r a_rc)|  (augmented column c = k holds w_r b_r).  One HBM pass; the maxima of
+//                         ALL slabs come from one launch in front of the slab loop (blockIdx.z = slab).
 //   2. i8_convert_kernel  q_rc = rint(fl(w_r a_rc) * 2^e_c), e_c = BETA-1-ilogb(m_c), an integer of at most
 //                         BETA <= 53 bits: the fp64 value itself when the column maximum has that exponent,
 //                         an absolute truncation at m_c 2^-BETA otherwise (what an fp64 dot product keeps of
@@ -13,8 +14,11 @@
 //                         residues q mod p_t as int8 planes  R_t[c][r]  (row index contiguous: both MMA
 //                         operands become K-major).  q is split into its 7 low bytes + sign and two
 //                         dp4a instructions per modulus fold them with the byte weights 256^i mod p_t; the
-//                         sum is then reduced with three fp32 operations (see I8Tables) -- no division, no
-//                         integer<->float conversion.  No shared memory: a warp owns 4 columns x 128 rows.
+//                         sum is then reduced with one fp32 fma and one integer multiply-add on the float's bit
+//                         pattern (see convert_one_modulus) -- no division, no integer<->float conversion.
+//                         No shared memory: a warp owns 4 columns x 128 rows.  (The same code can run as
+//                         converter warps inside the tensor-core kernel -- FSB_I8_CONVERTERS, off by default:
+//                         measured slower under the power cap)
 //   3. i8_gemm_kernel     for every modulus and every 128 x 256 tile of the lower triangle:
 //                         C_t = R_t^T R_t  with tcgen05.mma.kind::i8 (M128 N256 K32, int32 accumulators in
 //                         TMEM, operands TMA-loaded with 128-byte swizzle into a 4-stage mbarrier ring; one
@@ -28,7 +32,7 @@
 //
 // The result is the correctly rounded Gram of the quantised slab: independent of summation order, tile
 // shape (and, per slab, of the row order), at least as accurate normwise as the DMMA path
-// (tests/test_gpu_gram_int8.py).  Measured: DESIGN.md section 3.1a, profiles/r01_i8_gram_k1000.txt.
+// (tests/test_gpu_gram_int8.py).  Measured: DESIGN.md section 3.1a, profiles/r01_i8_gram_k1000.txt, r02_i8_k1000.txt.
 // References: solvers/svd.py:35-53, solvers/ridge.py:28-43 (the products this replaces).
 #include "fsb_common.cuh"
 #include <cuda.h>
