@@ -258,13 +258,30 @@ __global__ void __launch_bounds__(256) trsm_gemm_kernel(FactorView f, int p) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  constexpr int EPT = NB * MH / 256;          // next half prefetched into registers, as in syrk_update_kernel
+  double ra[EPT], rb[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int idx = threadIdx.x + 256 * e, r = idx / MH, c = idx % MH;
+    ra[e] = pa[(size_t)r * kp + c];
+    rb[e] = pb[(size_t)r * f.kp2 + c];
+  }
   for (int mh = 0; mh < NB; mh += MH) {
-    for (int idx = threadIdx.x; idx < NB * MH; idx += blockDim.x) {
-      const int r = idx / MH, c = idx % MH;
-      la[r][c] = pa[(size_t)r * kp + mh + c];
-      lb[r][c] = pb[(size_t)r * f.kp2 + mh + c];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int idx = threadIdx.x + 256 * e, r = idx / MH, c = idx % MH;
+      la[r][c] = ra[e];
+      lb[r][c] = rb[e];
     }
     __syncthreads();
+    if (mh + MH < NB) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int idx = threadIdx.x + 256 * e, r = idx / MH, c = idx % MH;
+        ra[e] = pa[(size_t)r * kp + mh + MH + c];
+        rb[e] = pb[(size_t)r * f.kp2 + mh + MH + c];
+      }
+    }
     for (int m = 0; m < MH; ++m) {
       double a[4], b[4];
 #pragma unroll
@@ -333,13 +350,32 @@ __global__ void __launch_bounds__(256) syrk_update_kernel(FactorView f, int p) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  // the next 32-column half is loaded into registers while the current one is multiplied (these kernels are a chain
+  // of dependent launches of ~20 us each: the global-load latency of a chunk was not overlapped with anything)
+  constexpr int EPT = NB * MH / 256;
+  double ra[EPT], rb[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int idx = threadIdx.x + 256 * e, r = idx / MH, c = idx % MH;
+    ra[e] = __ldg(pa + (size_t)r * kp + c);
+    rb[e] = __ldg(pb + (size_t)r * kp + c);
+  }
   for (int mh = 0; mh < NB; mh += MH) {
-    for (int idx = threadIdx.x; idx < NB * MH; idx += blockDim.x) {
-      const int r = idx / MH, c = idx % MH;
-      la[r][c] = __ldg(pa + (size_t)r * kp + mh + c);
-      lb[r][c] = __ldg(pb + (size_t)r * kp + mh + c);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int idx = threadIdx.x + 256 * e, r = idx / MH, c = idx % MH;
+      la[r][c] = ra[e];
+      lb[r][c] = rb[e];
     }
     __syncthreads();
+    if (mh + MH < NB) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int idx = threadIdx.x + 256 * e, r = idx / MH, c = idx % MH;
+        ra[e] = __ldg(pa + (size_t)r * kp + mh + MH + c);
+        rb[e] = __ldg(pb + (size_t)r * kp + mh + MH + c);
+      }
+    }
     for (int m = 0; m < MH; ++m) {
       double a[4], b[4];
 #pragma unroll
@@ -745,14 +781,33 @@ __device__ __forceinline__ void tile_gemm(const TileGemm& g) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
   if (!g.a_zero) {
-    for (int m0 = g.kb0 * NB; m0 < g.kb1 * NB; m0 += MH) {
-      for (int idx = threadIdx.x; idx < NB * MH; idx += blockDim.x) {
-        const int r = idx / MH, c = idx % MH;
-        sa[r][c] = g.a[(size_t)r * g.lda + m0 + c];
-        const int r2 = idx / NB, c2 = idx % NB;
-        sb[r2][c2] = g.b[(size_t)(m0 + r2) * g.ldb + c2];
+    constexpr int EPT = NB * MH / 256;        // the next 16-wide chunk is loaded while the current one is multiplied
+    double ra[EPT], rb[EPT];
+    const int mbeg = g.kb0 * NB, mend = g.kb1 * NB;
+    if (mbeg < mend) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int idx = threadIdx.x + 256 * e;
+        ra[e] = g.a[(size_t)(idx / MH) * g.lda + mbeg + idx % MH];
+        rb[e] = g.b[(size_t)(mbeg + idx / NB) * g.ldb + idx % NB];
+      }
+    }
+    for (int m0 = mbeg; m0 < mend; m0 += MH) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int idx = threadIdx.x + 256 * e;
+        sa[idx / MH][idx % MH] = ra[e];
+        sb[idx / NB][idx % NB] = rb[e];
       }
       __syncthreads();
+      if (m0 + MH < mend) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          const int idx = threadIdx.x + 256 * e;
+          ra[e] = g.a[(size_t)(idx / MH) * g.lda + m0 + MH + idx % MH];
+          rb[e] = g.b[(size_t)(m0 + MH + idx / NB) * g.ldb + idx % NB];
+        }
+      }
 #pragma unroll
       for (int m = 0; m < MH; ++m) {
         double a[4], b[4];
