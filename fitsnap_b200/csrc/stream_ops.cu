@@ -509,7 +509,7 @@ int launch_rowpass(const fsb_context* h, const double* A, int64_t lda, const dou
   else if (npl <= 2) FSB_ROWPASS(2, 4);
   else if (npl <= 4) { if (getenv("FSB_ROWPASS_RPI8")) FSB_ROWPASS_M(4, 8, 1); else FSB_ROWPASS(4, 4); }
   else if (npl <= 8) FSB_ROWPASS(8, 2);
-  else if (npl <= 16) FSB_ROWPASS1(16, 1);
+  else if (npl <= 16) FSB_ROWPASS1(16, 2);   // two rows per warp iteration: 8 KB in flight per warp, as at npl = 32
   else if (npl <= 32) FSB_ROWPASS1(32, 1);
   else if (npl <= 64) FSB_ROWPASS1(64, 1);
   else return FSB_ERR_UNSUPPORTED;   // k > 2048
