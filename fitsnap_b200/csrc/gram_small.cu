@@ -294,12 +294,12 @@ struct FusedArgs {
   int64_t total;            // rows of this call
   int64_t rows_per_cta;
   double* partial;
-  const struct FusedDesc* desc;   // per-row descriptors (row_resolve_kernel)
+  const struct FusedDesc* desc;   // per-row descriptors (row_resolve_body)
   int store_a;              // 0: streaming mode, A is not materialised (b and w still are)
-  int spec_from_a;          // 1: the energy / virial rows of A were written by special_rows_kernel before this launch
+  int spec_from_a;          // 1: the energy / virial rows of A were written by special_rows_body before this launch
 };
 
-struct FusedDesc {           // one per output row, written by row_resolve_kernel
+struct FusedDesc {           // one per output row, written by row_resolve_body
   double wg;                 // weight seen by the Gram: w, or 0 for a test row
   double div;                // N (energy row), V (virial row), 1 (force row)
   int kind;                  // 0 energy, 1 force, 2 virial
@@ -309,9 +309,9 @@ struct FusedDesc {           // one per output row, written by row_resolve_kerne
 // Row metadata is a chain of dependent global loads (row -> configuration -> offsets / weights / truth -> stress
 // component): resolved here for every row at once -- b and w are final after this kernel, the fused kernel below reads
 // one 24-byte descriptor per row.  ~1e6 rows: tens of microseconds, 2 % of the fused kernel's traffic.
-__global__ void __launch_bounds__(256) row_resolve_kernel(ScatterArgs a, const uint8_t* __restrict__ testing, int64_t total,
-                                                          FusedDesc* __restrict__ desc) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void row_resolve_body(const ScatterArgs& a, const uint8_t* __restrict__ testing, int64_t total,
+                                                 FusedDesc* __restrict__ desc, int64_t block) {
+  const int64_t i = block * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const bool do_scrub = a.flags & FSB_SCRUB_NONFINITE;
   const int kraw = a.ncoeff * a.numtypes;
@@ -359,12 +359,12 @@ __global__ void __launch_bounds__(256) row_resolve_kernel(ScatterArgs a, const u
 // division chains did not help, the pipe serialises them).  With this kernel the producers issue no fp64 operation
 // at all for these rows: they copy the finished values from A (L2-resident, written microseconds earlier) into the
 // DMMA ring.
-__global__ void __launch_bounds__(256) special_rows_kernel(ScatterArgs a) {
+__device__ __forceinline__ void special_rows_body(const ScatterArgs& a, int cfg_block) {
   // one CTA per configuration: its 7 special rows x k columns are dealt to the 256 threads (<= 3 elements each for
   // k <= 104), the per-configuration scalars are loaded once and every thread's raw loads are issued together -- with
   // one 128-thread CTA per ROW the kernel was a chain of dependent loads over 70 000 tiny CTAs (60 us at 1e4
   // configurations, a tenth of the fused phase)
-  const int cfg = blockIdx.x;
+  const int cfg = cfg_block;
   const bool bzero = a.flags & FSB_BZEROFLAG, do_scrub = a.flags & FSB_SCRUB_NONFINITE;
   const int kraw = a.ncoeff * a.numtypes;
   const int k = bzero ? kraw : kraw + a.numtypes;
@@ -411,6 +411,15 @@ __device__ __noinline__ double fused_special_row(double x, int kind, double div,
   if (kind == 1) return (loads_raw ? x : 0.0) * pref;                                   // lammps_snap.py:493-502
   if (kind == 2) return (loads_raw ? (FSB_VIRIAL_UNIT * x) / div : 0.0) * pref;         // :526-536
   return (loads_raw ? x / div : tf) * pref;                                             // :435-467
+}
+
+// The two preparation steps of the fused kernel in ONE launch (they are independent: blocks [0, nspecial) finish the
+// energy / virial rows of one configuration each, the others resolve 256 row descriptors each), so that the ~20 us of
+// the first hide behind the ~28 us of the second instead of preceding them.
+__global__ void __launch_bounds__(256) fused_prep_kernel(ScatterArgs a, const uint8_t* __restrict__ testing, int64_t total,
+                                                         FusedDesc* __restrict__ desc, int nspecial) {
+  if ((int64_t)blockIdx.x < (int64_t)nspecial) special_rows_body(a, (int)blockIdx.x);
+  else row_resolve_body(a, testing, total, desc, (int64_t)blockIdx.x - nspecial);
 }
 
 __device__ __forceinline__ unsigned fz_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -631,7 +640,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p,
       if (do_scrub && __any_sync(0xffffffffu, nf != 0u)) redo = valid;           // numpy.nan_to_num: rare
       if (redo) {
         arow = a.A + (row0 + row_begin + (int64_t)s * S_RCH) * a.lda + c;
-        unsigned copy = redo & spec_mask;                        // finished by special_rows_kernel: A -> ring
+        unsigned copy = redo & spec_mask;                        // finished by special_rows_body: A -> ring
         redo &= ~spec_mask;
         while (copy) {                                           // warp-uniform; 8 independent loads per batch
           int jj[8];
@@ -673,7 +682,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) scatter_gram_kernel(FusedArgs p,
       bar_arrive(1 + (s % nstage_d), S_THREADS);                               // FULL[slot] of the DMMA ring
       if (p.spec_from_a) {
         // the finished energy / virial rows of the NEXT stage: pull them towards this SM now (they were written by
-        // special_rows_kernel and have usually left L2 again), so that the copy loop above does not wait on DRAM
+        // special_rows_body and have usually left L2 again), so that the copy loop above does not wait on DRAM
         unsigned nxt = __ballot_sync(0xffffffffu, dB.kind == 0 || dB.kind == 2);
         const double* nrow = a.A + (row0 + row_begin + (int64_t)(s + 1) * S_RCH) * a.lda + c;
         while (nxt) {
@@ -776,15 +785,13 @@ int fsb_launch_scatter_gram_small(const fsb_context* h, const ScatterArgs& sc, c
   FusedArgs a;
   a.sc = sc; a.testing = testing; a.total = total; a.partial = partial; a.store_a = store_a;
   a.desc = (const FusedDesc*)desc;
-  row_resolve_kernel<<<(unsigned)fsb_ceil_div(total, 256), 256, 0, s>>>(sc, testing, total, (FusedDesc*)desc);
-  FSB_LAUNCH_CHECK("row_resolve_kernel");
   static int no_pre = -1;          // development switch: the divisions of the special rows inside the fused kernel
   if (no_pre < 0) no_pre = getenv("FSB_FUSED_NO_PRESPECIAL") ? 1 : 0;
   a.spec_from_a = (store_a && sc.A && sc.ncfg > 0 && !no_pre) ? 1 : 0;
-  if (a.spec_from_a) {
-    special_rows_kernel<<<(unsigned)sc.ncfg, 256, 0, s>>>(sc);
-    FSB_LAUNCH_CHECK("special_rows_kernel");
-  }
+  const int nspecial = a.spec_from_a ? sc.ncfg : 0;
+  fused_prep_kernel<<<(unsigned)(nspecial + fsb_ceil_div(total, 256)), 256, 0, s>>>(sc, testing, total, (FusedDesc*)desc,
+                                                                                   nspecial);
+  FSB_LAUNCH_CHECK("fused_prep_kernel");
   const int want = fsb_gram_small_ctas(h, total);
   a.rows_per_cta = fsb_round_up(fsb_ceil_div(total > 0 ? total : 1, want), S_RCH);
   switch (nb) {
